@@ -1,0 +1,218 @@
+"""ctypes binding of include/bnmf.h.  There is no CPU path: if the CUDA library is
+missing, or no GPU is visible when a sampler is created, this fails loudly."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbnmf_b200.so")
+
+POISSON, NORMAL = 0, 1
+TRUNCNORMAL, EXPONENTIAL, GAMMA = 0, 1, 2
+SBFI, BFI, BIC = 0, 1, 2
+F64, F32 = 0, 1
+LIKELIHOODS = {"poisson": POISSON, "normal": NORMAL}
+PRIORS = {"truncnormal": TRUNCNORMAL, "exponential": EXPONENTIAL, "gamma": GAMMA}
+RANK_METHODS = {"SBFI": SBFI, "BFI": BFI, "BIC": BIC}
+MC_COLS = 11
+METRIC_NAMES = ["iter", "RMSE", "KL", "loglikelihood", "logposterior", "n_params", "BIC", "rank", "temp",
+                "P_mean_acceptance_rate", "E_mean_acceptance_rate"]
+HAVE = {"P": 1, "E": 2, "A": 4, "Z": 8, "sigmasq": 16}
+# have_prior bits: 0..4 = Mu,Sigmasq,Lambda,Alpha,Beta on the P side, 8..12 on the E side
+HAVE_PRIOR = {"Mu_p": 1 << 0, "Sigmasq_p": 1 << 1, "Lambda_p": 1 << 2, "Alpha_p": 1 << 3, "Beta_p": 1 << 4,
+              "Mu_e": 1 << 8, "Sigmasq_e": 1 << 9, "Lambda_e": 1 << 10, "Alpha_e": 1 << 11, "Beta_e": 1 << 12}
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("K", ctypes.c_int32), ("N", ctypes.c_int32), ("G", ctypes.c_int64),
+                ("G_total", ctypes.c_int64), ("g0", ctypes.c_int64),
+                ("likelihood", ctypes.c_int32), ("prior", ctypes.c_int32), ("MH", ctypes.c_int32),
+                ("learning_rank", ctypes.c_int32), ("rank_method", ctypes.c_int32),
+                ("precision", ctypes.c_int32), ("device", ctypes.c_int32), ("ring_cap", ctypes.c_int32),
+                ("seed", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+class BnmfError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libbnmf_b200.so (built in-tree by bayesnmf_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BnmfError(
+            f"{LIB_PATH} not found: build it with `python -m bayesnmf_b200.build` "
+            "(nvcc, sm_100a).  bayesnmf_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, cp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.bnmf_last_error.restype = cp
+    L.bnmf_check_model.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, cp, ctypes.c_size_t]
+    L.bnmf_create.argtypes = [ctypes.POINTER(Config), dp, ctypes.POINTER(vp)]
+    L.bnmf_destroy.argtypes = [vp]
+    L.bnmf_destroy.restype = None
+    L.bnmf_set_hyper.argtypes = [vp, cp, dp, i64, i64]
+    L.bnmf_set_state.argtypes = [vp, cp, dp, i64]
+    L.bnmf_get_state.argtypes = [vp, cp, dp, i64]
+    L.bnmf_set_temperature_schedule.argtypes = [vp, dp, i64]
+    L.bnmf_init_from_prior.argtypes = [vp, u32, u32, dp]
+    L.bnmf_step.argtypes = [vp, i32, i32, dp, dp, dp]
+    L.bnmf_ring_count.argtypes = [vp, ctypes.POINTER(i32)]
+    L.bnmf_get_sample.argtypes = [vp, cp, i32, dp, i64]
+    L.bnmf_get_map.argtypes = [vp, i32, dp, dp, dp, ctypes.POINTER(i32)]
+    L.bnmf_comm_unique_id.argtypes = [ctypes.c_char_p]
+    L.bnmf_comm_init.argtypes = [vp, ctypes.c_char_p, i32, i32]
+    L.bnmf_timing.argtypes = [vp, dp, dp, ctypes.POINTER(i64)]
+    L.bnmf_sample_z.argtypes = [vp, i32, dp]
+    _lib = L
+    return L
+
+
+EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
+           "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
+           "bnmf_step", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_comm_unique_id",
+           "bnmf_comm_init", "bnmf_timing", "bnmf_sample_z"]
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _f64(a):
+    """Column-major (R layout) contiguous float64 copy, flattened."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).T).reshape(-1) if np.ndim(a) == 2 \
+        else np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(-1)
+
+
+class Handle:
+    """Thin owner of a bnmf_handle*; shapes follow the reference (K x N, N x G)."""
+
+    def __init__(self, data, N, likelihood="poisson", prior="gamma", MH=False, learning_rank=False,
+                 rank_method="SBFI", seed=0, precision="f64", device=0, ring_cap=0, g0=0, G_total=None):
+        L = lib()
+        data = np.asarray(data, dtype=np.float64)
+        self.K, self.G = data.shape
+        self.N = int(N)
+        cfg = Config(K=self.K, N=self.N, G=self.G, G_total=self.G if G_total is None else int(G_total), g0=int(g0),
+                     likelihood=LIKELIHOODS[likelihood], prior=PRIORS[prior], MH=int(bool(MH)),
+                     learning_rank=int(bool(learning_rank)), rank_method=RANK_METHODS[rank_method],
+                     precision=F64 if precision == "f64" else F32, device=int(device), ring_cap=int(ring_cap),
+                     seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+        self.cfg = cfg
+        self._h = ctypes.c_void_p()
+        flat = _f64(data)
+        self._ck(L.bnmf_create(ctypes.byref(cfg), _dp(flat), ctypes.byref(self._h)))
+        self.shapes = {
+            "P": (self.K, self.N), "E": (self.N, self.G), "A": (self.N,), "R": (1,), "sigmasq": (self.G,),
+            "SP": (self.K, self.N), "SE": (self.N, self.G), "Alpha": (self.G,), "Beta": (self.G,),
+            "P_acceptance_rate": (self.K, self.N), "E_acceptance_rate": (self.N, self.G),
+            "Mhat": (self.K, self.G), "rowsumE": (self.N,),
+        }
+        for nm in ("Mu", "Sigmasq", "Lambda", "Alpha", "Beta"):
+            self.shapes[nm + "_p"] = (self.K, self.N)
+            self.shapes[nm + "_e"] = (self.N, self.G)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BnmfError(lib().bnmf_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().bnmf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_hyper(self, name, value):
+        v = np.asarray(value, dtype=np.float64)
+        if v.ndim == 0 or v.size == 1:
+            flat = v.reshape(1).copy()
+            self._ck(lib().bnmf_set_hyper(self._h, name.encode(), _dp(flat), 1, 1))
+        else:
+            flat = _f64(v)
+            self._ck(lib().bnmf_set_hyper(self._h, name.encode(), _dp(flat), v.shape[0], v.shape[1]))
+
+    def set_state(self, name, value):
+        flat = _f64(np.asarray(value, dtype=np.float64).reshape(self.shapes[name]))
+        self._ck(lib().bnmf_set_state(self._h, name.encode(), _dp(flat), flat.size))
+
+    def get_state(self, name):
+        shp = self.shapes[name]
+        n = int(np.prod(shp))
+        out = np.empty(n, dtype=np.float64)
+        self._ck(lib().bnmf_get_state(self._h, name.encode(), _dp(out), n))
+        return out.reshape(shp[::-1]).T.copy() if len(shp) == 2 else out
+
+    def set_temperature_schedule(self, temps):
+        t = np.ascontiguousarray(np.asarray(temps, dtype=np.float64))
+        self._ck(lib().bnmf_set_temperature_schedule(self._h, _dp(t), t.size))
+
+    def init_from_prior(self, have=(), have_prior=()):
+        hv = sum(HAVE[h] for h in have if h in HAVE)
+        hp = sum(HAVE_PRIOR[h] for h in have_prior if h in HAVE_PRIOR)
+        row = np.empty(MC_COLS)
+        self._ck(lib().bnmf_init_from_prior(self._h, hv, hp, _dp(row)))
+        return dict(zip(METRIC_NAMES, row))
+
+    def step(self, n_iters, converged=False, want_P=False, want_A=False):
+        n_iters = int(n_iters)
+        met = np.empty((n_iters, MC_COLS))
+        P = np.empty(n_iters * self.K * self.N) if want_P else None
+        A = np.empty(n_iters * self.N) if want_A else None
+        self._ck(lib().bnmf_step(self._h, n_iters, int(bool(converged)), _dp(met),
+                                 _dp(P) if want_P else None, _dp(A) if want_A else None))
+        out = {"metrics": met}
+        if want_P:
+            out["P"] = P.reshape(n_iters, self.N, self.K).transpose(0, 2, 1)
+        if want_A:
+            out["A"] = A.reshape(n_iters, self.N)
+        return out
+
+    def ring_count(self):
+        c = ctypes.c_int32()
+        self._ck(lib().bnmf_ring_count(self._h, ctypes.byref(c)))
+        return c.value
+
+    def get_sample(self, name, ago=0):
+        shp = self.shapes[name]
+        n = int(np.prod(shp))
+        out = np.empty(n)
+        self._ck(lib().bnmf_get_sample(self._h, name.encode(), int(ago), _dp(out), n))
+        return out.reshape(shp[::-1]).T.copy() if len(shp) == 2 else out
+
+    def get_map(self, n_samples):
+        P = np.empty(self.K * self.N); E = np.empty(self.N * self.G); A = np.empty(self.N)
+        nm = ctypes.c_int32()
+        self._ck(lib().bnmf_get_map(self._h, int(n_samples), _dp(P), _dp(E), _dp(A), ctypes.byref(nm)))
+        return P.reshape(self.N, self.K).T.copy(), E.reshape(self.G, self.N).T.copy(), A, nm.value
+
+    def comm_init(self, uid, rank, world):
+        self._ck(lib().bnmf_comm_init(self._h, uid, int(rank), int(world)))
+
+    def timing(self):
+        t = ctypes.c_double(); z = ctypes.c_double(); l = ctypes.c_int64()
+        self._ck(lib().bnmf_timing(self._h, ctypes.byref(t), ctypes.byref(z), ctypes.byref(l)))
+        return {"total_ms": t.value, "zstat_ms": z.value, "launches": l.value}
+
+    def sample_z(self, it):
+        ms = ctypes.c_double()
+        self._ck(lib().bnmf_sample_z(self._h, int(it), ctypes.byref(ms)))
+        return ms.value
+
+
+def comm_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    rc = lib().bnmf_comm_unique_id(buf)
+    if rc != 0:
+        raise BnmfError(lib().bnmf_last_error().decode())
+    return buf.raw

@@ -1,0 +1,683 @@
+// C ABI of bayesnmf_b200 (include/bnmf.h): handle management, state I/O and the
+// per-iteration launch sequence.  No torch, no Rcpp; built by nvcc for sm_100a.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bnmf.h"
+#include "bnmf_init.cuh"
+#include "bnmf_mh.cuh"
+#include "bnmf_poisson.cuh"
+#include "bnmf_state.h"
+
+using namespace bnmf;
+
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return 1;
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail("%s:%d CUDA error %s (%s)", __FILE__, __LINE__, cudaGetErrorName(e_), cudaGetErrorString(e_)); } while (0)
+
+// ---------------------------------------------------------------------------------
+// NCCL through dlopen: the library itself has no link-time dependency on it.
+// ---------------------------------------------------------------------------------
+struct Id128 { char b[128]; };
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value (128 bytes)*/ Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) return fail("NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+#define LD(field, sym) *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, sym); if (!g_nccl.field) return fail("NCCL symbol %s missing", sym)
+  LD(GetUniqueId, "ncclGetUniqueId");
+  LD(CommInitRank, "ncclCommInitRank");
+  LD(AllReduce, "ncclAllReduce");
+  LD(GroupStart, "ncclGroupStart");
+  LD(GroupEnd, "ncclGroupEnd");
+  LD(CommDestroy, "ncclCommDestroy");
+  LD(GetErrorString, "ncclGetErrorString");
+#undef LD
+  return 0;
+}
+enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_INT32 = 2 };
+
+// ---------------------------------------------------------------------------------
+struct bnmf_handle {
+  virtual ~bnmf_handle() {}
+  virtual int set_hyper(const char* name, const double* v, int64_t rows, int64_t cols) = 0;
+  virtual int set_state(const char* name, const double* v, int64_t len) = 0;
+  virtual int get_state(const char* name, double* out, int64_t len) = 0;
+  virtual int set_temps(const double* t, int64_t n) = 0;
+  virtual int init_from_prior(uint32_t have, uint32_t have_prior, double* row) = 0;
+  virtual int step(int n_iters, int converged, double* metrics, double* P_out, double* A_out) = 0;
+  virtual int ring_count(int* c) = 0;
+  virtual int get_sample(const char* name, int ago, double* out, int64_t len) = 0;
+  virtual int get_map(int n_samples, double* P, double* E, double* A, int* n_match) = 0;
+  virtual int comm_init(const char* id, int rank, int world) = 0;
+  virtual int timing(double* total, double* z, int64_t* launches) = 0;
+  virtual int sample_z(int iter, double* ms) = 0;
+};
+
+template <typename T> static __global__ void k_cvt_in(const double* src, T* dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (T)src[i];
+}
+template <typename S> static __global__ void k_cvt_out(const S* src, double* dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+static __global__ void k_cvt_in_i32(const double* src, int32_t* dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (int32_t)llrint(src[i]);
+}
+static __global__ void k_cvt_in_u64(const double* src, unsigned long long* dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (unsigned long long)llrint(src[i]);
+}
+// data constants of the Poisson likelihood / padded KL (R/utils.R:103, :467-471)
+static __global__ void k_data_consts(const int32_t* Mi, long long n, double* out /*2*/) {
+  __shared__ double sc[8];
+  double ll = 0.0, kl = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double m = (double)Mi[i];
+    ll -= lgamma(m + 1.0);
+    double mp = m > 1e-6 ? m : 1e-6;
+    kl += mp * log(mp);
+  }
+  double a = block_sum<256>(ll, sc);
+  double b = block_sum<256>(kl, sc);
+  if (threadIdx.x == 0) { out[2 * blockIdx.x] = a; out[2 * blockIdx.x + 1] = b; }
+}
+
+enum StType { ST_T, ST_I32, ST_U64 };
+struct StEntry { void* p; long long len; StType ty; };
+
+template <typename T>
+struct Sampler : bnmf_handle {
+  bnmf_config cfg;
+  Dev<T> d;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  std::map<std::string, StEntry> st;
+  std::map<std::string, Hyper<T>*> hy;
+  std::map<std::string, long long> hy_len;
+  double* stage = nullptr; long long stage_len = 0;      // device double staging
+  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96;
+  int* nanflags = nullptr;
+  T* P_hist = nullptr; int32_t* A_hist = nullptr;
+  double* h_metrics = nullptr;                            // pinned
+  int NP = 0; size_t z_smem = 0;
+  void* comm = nullptr; int world = 1, rank = 0;
+  long long* red_i64 = nullptr;                           // [K*N + N] packed int64 reduction buffer
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> zev;
+  bool time_z = true;
+  double last_total_ms = 0, last_z_ms = 0; int64_t last_launches = 0;
+  bool have_temps = false;
+
+  ~Sampler() override {
+    cudaSetDevice(cfg.device);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    for (void* p : allocs) cudaFree(p);
+    if (h_metrics) cudaFreeHost(h_metrics);
+    for (auto e : zev) cudaEventDestroy(e);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  template <typename X> int dalloc(X** p, long long n) {
+    if (n < 1) n = 1;
+    CK(cudaMalloc((void**)p, (size_t)n * sizeof(X)));
+    CK(cudaMemsetAsync(*p, 0, (size_t)n * sizeof(X), stream));
+    allocs.push_back(*p);
+    return 0;
+  }
+  int reg(const char* name, T** p, long long n) {
+    if (dalloc(p, n)) return 1;
+    st[name] = StEntry{*p, n, ST_T};
+    return 0;
+  }
+  int ensure_stage(long long n) {
+    if (n <= stage_len) return 0;
+    if (stage) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(stage)); for (auto& a : allocs) if (a == stage) a = nullptr; }
+    CK(cudaMalloc((void**)&stage, (size_t)n * sizeof(double)));
+    allocs.push_back(stage);
+    stage_len = n;
+    return 0;
+  }
+  static int blocks(long long n, int t) { return (int)((n + t - 1) / t); }
+
+  int create(const bnmf_config* c, const double* data) {
+    cfg = *c;
+    if (cfg.K < 1 || cfg.N < 1 || cfg.G < 1) return fail("bnmf_create: K, N, G must be >= 1");
+    if (cfg.N > 64) return fail("bnmf_create: N = %d > 64 is not supported by this build", cfg.N);
+    if (cfg.G > 2000000000LL / (cfg.K > cfg.N ? cfg.K : cfg.N)) { /* 64-bit indexing is used throughout; fine */ }
+    CK(cudaSetDevice(cfg.device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    memset(&d, 0, sizeof(d));
+    const int K = cfg.K, N = cfg.N; const long long G = cfg.G;
+    d.K = K; d.N = N; d.G = (int)G; d.G_total = cfg.G_total; d.g0 = cfg.g0;
+    d.likelihood = cfg.likelihood; d.prior = cfg.prior; d.MH = cfg.MH;
+    d.learning_rank = cfg.learning_rank; d.rank_method = cfg.rank_method; d.seed = cfg.seed;
+    const long long KN = (long long)K * N, NG = (long long)N * G, KG = (long long)K * G;
+
+    // parameters
+    if (reg("P", &d.P, KN) || reg("E", &d.E, NG) || reg("sigmasq", &d.sigmasq, G)) return 1;
+    if (dalloc(&d.A, N) || dalloc(&d.R, 1)) return 1;
+    st["A"] = StEntry{d.A, N, ST_I32}; st["R"] = StEntry{d.R, 1, ST_I32};
+    // prior parameters (all allocated: cheap relative to E, keeps the name table uniform)
+    if (reg("Mu_p", &d.Mu_p, KN) || reg("Sigmasq_p", &d.Sigmasq_p, KN) || reg("Lambda_p", &d.Lambda_p, KN) ||
+        reg("Alpha_p", &d.Alpha_p, KN) || reg("Beta_p", &d.Beta_p, KN)) return 1;
+    if (cfg.prior == BNMF_TRUNCNORMAL) { if (reg("Mu_e", &d.Mu_e, NG) || reg("Sigmasq_e", &d.Sigmasq_e, NG)) return 1; }
+    if (cfg.prior == BNMF_EXPONENTIAL) { if (reg("Lambda_e", &d.Lambda_e, NG)) return 1; }
+    if (cfg.prior == BNMF_GAMMA) { if (reg("Alpha_e", &d.Alpha_e, NG) || reg("Beta_e", &d.Beta_e, NG)) return 1; }
+    if (cfg.likelihood == BNMF_NORMAL) { if (reg("Alpha", &d.Alpha_g, G) || reg("Beta", &d.Beta_g, G)) return 1; }
+    // hyperparameters: start as scalars (1 element), may be replaced by matrices
+    struct HN { const char* n; Hyper<T>* h; long long len; };
+    HN hn[] = {{"A_p", &d.A_p, KN}, {"B_p", &d.B_p, KN}, {"C_p", &d.C_p, KN}, {"D_p", &d.D_p, KN},
+               {"M_p", &d.M_p, KN}, {"S_p", &d.S_p, KN}, {"A_e", &d.A_e, NG}, {"B_e", &d.B_e, NG},
+               {"C_e", &d.C_e, NG}, {"D_e", &d.D_e, NG}, {"M_e", &d.M_e, NG}, {"S_e", &d.S_e, NG}};
+    for (auto& h : hn) {
+      T* p; if (dalloc(&p, 1)) return 1;
+      h.h->p = p; h.h->is_matrix = 0; hy[h.n] = h.h; hy_len[h.n] = h.len;
+    }
+    // statistics / reductions
+    if (dalloc(&red_i64, KN + N)) return 1;
+    d.SP = (unsigned long long*)red_i64; d.rowsumE_fx = red_i64 + KN;
+    st["SP"] = StEntry{d.SP, KN, ST_U64};
+    if (dalloc(&d.SE, NG)) return 1;
+    st["SE"] = StEntry{d.SE, NG, ST_I32};
+    if (dalloc(&d.colsumP, N) || dalloc(&d.lp_P, 1) || dalloc(&d.pacc_sum, 1)) return 1;
+    if (cfg.MH) { if (reg("P_acceptance_rate", &d.P_acc, KN) || reg("E_acceptance_rate", &d.E_acc, NG)) return 1; }
+    if (cfg.MH || cfg.likelihood == BNMF_NORMAL || cfg.learning_rank) { if (reg("Mhat", &d.Mhat, KG)) return 1; }
+
+    // work decomposition of the column kernels
+    KT = ((K + 31) / 32) * 32; if (KT > 128) KT = 128;
+    n_ktiles = (K + KT - 1) / KT;
+    const int cts = (int)((G + 31) / 32);
+    d.n_zitems = cts * n_ktiles * ((KT + 31) / 32);
+    d.n_eblocks = blocks(NG, 256);
+    if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
+        dalloc(&d.red, PC_COLS) || dalloc(&work_ctr, n_ktiles + 8) || dalloc(&nanflags, 5 * N)) return 1;
+    if (dalloc(&d.ctrl, 1)) return 1;
+    d.metrics_cap = 256;
+    if (dalloc(&d.metrics, (long long)d.metrics_cap * MC_COLS)) return 1;
+    CK(cudaMallocHost((void**)&h_metrics, (size_t)d.metrics_cap * MC_COLS * sizeof(double)));
+    if (dalloc(&P_hist, (long long)d.metrics_cap * KN) || dalloc(&A_hist, (long long)d.metrics_cap * N)) return 1;
+    { double* t; if (dalloc(&t, 1)) return 1; d.temps = t; d.n_temps = 0; }
+    // ring
+    d.ring_cap = cfg.ring_cap > 0 ? cfg.ring_cap : 0;
+    if (d.ring_cap > 0) {
+      if (dalloc(&d.ring_P, (long long)d.ring_cap * KN) || dalloc(&d.ring_E, (long long)d.ring_cap * NG) ||
+          dalloc(&d.ring_A, (long long)d.ring_cap * N)) return 1;
+    }
+    // data
+    if (ensure_stage(KG)) return 1;
+    CK(cudaMemcpyAsync(stage, data, (size_t)KG * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (cfg.likelihood == BNMF_POISSON) {
+      for (long long i = 0; i < KG; ++i) {
+        double v = data[i];
+        if (!(v >= 0.0) || v != std::floor(v) || v > 2147483647.0)
+          return fail("bnmf_create: Poisson likelihood needs non-negative integer counts (data[%lld] = %g)", i, v);
+      }
+      int32_t* mi; if (dalloc(&mi, KG)) return 1;
+      k_cvt_in_i32<<<blocks(KG, 256), 256, 0, stream>>>(stage, mi, KG);
+      d.Mi = mi;
+      const int nb = 296;
+      double* cpart; if (dalloc(&cpart, 2 * nb)) return 1;
+      k_data_consts<<<nb, 256, 0, stream>>>(mi, KG, cpart);
+      std::vector<double> hc(2 * nb);
+      CK(cudaMemcpyAsync(hc.data(), cpart, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      double a = 0, b = 0;
+      for (int i = 0; i < nb; ++i) { a += hc[2 * i]; b += hc[2 * i + 1]; }
+      d.ll_const = a; d.kl_const = b;
+    } else {
+      T* mr; if (dalloc(&mr, KG)) return 1;
+      k_cvt_in<T><<<blocks(KG, 256), 256, 0, stream>>>(stage, mr, KG);
+      d.Mr = mr;
+      st["data"] = StEntry{mr, KG, ST_T};
+    }
+    // kernel configuration of k_zstat
+    NP = ((N + 3) / 4) * 4; if (NP > 32) NP = ((N + 7) / 8) * 8;
+    {
+      int np2 = NP <= 4 ? 4 : NP <= 8 ? 8 : NP <= 16 ? 16 : NP <= 32 ? 32 : 64;
+      z_smem = (size_t)KT * NP * sizeof(T) + (size_t)np2 * ZT * sizeof(T) + (size_t)NP * ZT * sizeof(int) +
+               (size_t)KT * N * sizeof(int);
+    }
+    if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (z_config()) return 1; }
+    if (mh_setup()) return 1;
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  // ---- k_zstat dispatch over the compile-time signature count -------------------
+  template <int NPV> int z_launch_t(bool configure) {
+    auto kern = k_zstat<T, NPV>;
+    if (configure) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem));
+      return 0;
+    }
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    int per_sm = NPV <= 32 ? 2 : 1;
+    int bx = dev_sms * per_sm / n_ktiles; if (bx < 1) bx = 1;
+    const long long items = (long long)((d.G + 31) / 32) * ((KT + 31) / 32);
+    long long need = (items + (ZT / 32) - 1) / (ZT / 32);
+    if (bx > need) bx = (int)need;
+    dim3 grid(bx, n_ktiles);
+    kern<<<grid, ZT, z_smem, stream>>>(d, KT, work_ctr);
+    return 0;
+  }
+  int z_dispatch(bool configure) {
+    switch (NP) {
+      case 4: return z_launch_t<4>(configure);
+      case 8: return z_launch_t<8>(configure);
+      case 12: return z_launch_t<12>(configure);
+      case 16: return z_launch_t<16>(configure);
+      case 20: return z_launch_t<20>(configure);
+      case 24: return z_launch_t<24>(configure);
+      case 28: return z_launch_t<28>(configure);
+      case 32: return z_launch_t<32>(configure);
+      case 40: return z_launch_t<40>(configure);
+      case 48: return z_launch_t<48>(configure);
+      case 56: return z_launch_t<56>(configure);
+      case 64: return z_launch_t<64>(configure);
+    }
+    return fail("k_zstat: unsupported padded signature count %d", NP);
+  }
+  int z_config() {
+    if (z_smem > 227 * 1024) return fail("k_zstat: %zu bytes of shared memory needed (K tile %d, N %d)", z_smem, KT, cfg.N);
+    return z_dispatch(true);
+  }
+
+  // ---- state I/O -------------------------------------------------------------------
+  int set_hyper(const char* name, const double* v, int64_t rows, int64_t cols) override {
+    CK(cudaSetDevice(cfg.device));
+    auto it = hy.find(name);
+    if (it == hy.end()) return fail("bnmf_set_hyper: unknown hyperparameter '%s'", name);
+    long long n = (long long)rows * cols;
+    long long full = hy_len[name];
+    if (n != 1 && n != full) return fail("bnmf_set_hyper: '%s' must be scalar or have %lld elements (got %lld)", name, full, n);
+    T* p; if (dalloc(&p, n)) return 1;
+    if (ensure_stage(n)) return 1;
+    CK(cudaMemcpyAsync(stage, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    k_cvt_in<T><<<blocks(n, 256), 256, 0, stream>>>(stage, p, n);
+    CK(cudaStreamSynchronize(stream));
+    it->second->p = p; it->second->is_matrix = n != 1;
+    return 0;
+  }
+  int set_state(const char* name, const double* v, int64_t len) override {
+    CK(cudaSetDevice(cfg.device));
+    auto it = st.find(name);
+    if (it == st.end()) return fail("bnmf_set_state: unknown or unallocated state '%s' for this model", name);
+    if (len != it->second.len) return fail("bnmf_set_state: '%s' has %lld elements, got %lld", name, it->second.len, (long long)len);
+    if (ensure_stage(len)) return 1;
+    CK(cudaMemcpyAsync(stage, v, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, stream));
+    const int b = blocks(len, 256);
+    if (it->second.ty == ST_T) k_cvt_in<T><<<b, 256, 0, stream>>>(stage, (T*)it->second.p, len);
+    else if (it->second.ty == ST_I32) k_cvt_in_i32<<<b, 256, 0, stream>>>(stage, (int32_t*)it->second.p, len);
+    else k_cvt_in_u64<<<b, 256, 0, stream>>>(stage, (unsigned long long*)it->second.p, len);
+    CK(cudaStreamSynchronize(stream));
+    if (!strcmp(name, "E")) { if (refresh_rowsumE()) return 1; }
+    if (!strcmp(name, "P")) { if (refresh_colsumP()) return 1; }
+    return 0;
+  }
+  int dev_to_host(const void* p, StType ty, long long len, double* out) {
+    if (ensure_stage(len)) return 1;
+    const int b = blocks(len, 256);
+    if (ty == ST_T) k_cvt_out<T><<<b, 256, 0, stream>>>((const T*)p, stage, len);
+    else if (ty == ST_I32) k_cvt_out<int32_t><<<b, 256, 0, stream>>>((const int32_t*)p, stage, len);
+    else k_cvt_out<unsigned long long><<<b, 256, 0, stream>>>((const unsigned long long*)p, stage, len);
+    CK(cudaMemcpyAsync(out, stage, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int get_state(const char* name, double* out, int64_t len) override {
+    CK(cudaSetDevice(cfg.device));
+    if (!strcmp(name, "rowsumE")) {
+      if (len != cfg.N) return fail("bnmf_get_state: 'rowsumE' has %d elements", cfg.N);
+      std::vector<long long> h(cfg.N);
+      CK(cudaMemcpyAsync(h.data(), d.rowsumE_fx, sizeof(long long) * cfg.N, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      for (int i = 0; i < cfg.N; ++i) out[i] = (double)h[i] / RS_FX;
+      return 0;
+    }
+    auto it = st.find(name);
+    if (it == st.end()) return fail("bnmf_get_state: unknown or unallocated state '%s' for this model", name);
+    if (len != it->second.len) return fail("bnmf_get_state: '%s' has %lld elements, got %lld", name, it->second.len, (long long)len);
+    return dev_to_host(it->second.p, it->second.ty, len, out);
+  }
+  int set_temps(const double* t, int64_t n) override {
+    CK(cudaSetDevice(cfg.device));
+    double* p; if (dalloc(&p, n)) return 1;
+    CK(cudaMemcpyAsync(p, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    d.temps = p; d.n_temps = (int)n; have_temps = true;
+    return 0;
+  }
+
+  // rowSums(E) / colSums(P) after a user-supplied state (fixed point for E)
+  int refresh_rowsumE();
+  int refresh_colsumP();
+
+  // ---- cross-shard sum -----------------------------------------------------------
+  int comm_init(const char* id, int rank_, int world_) override {
+    CK(cudaSetDevice(cfg.device));
+    if (load_nccl()) return 1;
+    Id128 uid; memcpy(uid.b, id, 128);
+    int r = g_nccl.CommInitRank(&comm, world_, uid, rank_);
+    if (r) return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    world = world_; rank = rank_;
+    return 0;
+  }
+  int allreduce_stats() {   // SP + rowsumE_fx (exact int64 sums)
+    if (world <= 1) return 0;
+    int r = g_nccl.AllReduce(red_i64, red_i64, (size_t)cfg.K * cfg.N + cfg.N, NCCL_INT64, NCCL_SUM, comm, stream);
+    if (r) return fail("ncclAllReduce(stats): %s", g_nccl.GetErrorString(r));
+    return 0;
+  }
+  int allreduce_red() {     // metric partials
+    if (world <= 1) return 0;
+    int r = g_nccl.AllReduce(d.red, d.red, PC_COLS, NCCL_FLOAT64, NCCL_SUM, comm, stream);
+    if (r) return fail("ncclAllReduce(metrics): %s", g_nccl.GetErrorString(r));
+    return 0;
+  }
+  int allreduce_buf(void* p, size_t n, int dtype, int op) {
+    if (world <= 1) return 0;
+    int r = g_nccl.AllReduce(p, p, n, dtype, op, comm, stream);
+    if (r) return fail("ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    return 0;
+  }
+
+  // ---- the iteration ---------------------------------------------------------------
+  int launches = 0;
+  int mh_setup();
+  int mh_iteration(int from_prior, uint32_t have);
+  int poisson_iteration(int from_prior, uint32_t have, cudaEvent_t z0, cudaEvent_t z1) {
+    const int keepP = (have & BNMF_HAVE_P) ? 1 : 0, keepE = (have & BNMF_HAVE_E) ? 1 : 0;
+    k_pside<T, 128><<<cfg.N, 128, 0, stream>>>(d, from_prior, keepP); ++launches;
+    k_eside<T, 256><<<d.n_eblocks, 256, 0, stream>>>(d, from_prior, keepE); ++launches;
+    if (allreduce_buf(d.rowsumE_fx, cfg.N, NCCL_INT64, NCCL_SUM)) return 1;
+    if (from_prior) { k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); ++launches; }
+    else if (cfg.learning_rank) { if (rank_sweep()) return 1; }
+    if (!(from_prior && (have & BNMF_HAVE_Z))) {
+      if (z0) CK(cudaEventRecord(z0, stream));
+      if (z_dispatch(false)) return 1; ++launches;
+      if (z1) CK(cudaEventRecord(z1, stream));
+      if (allreduce_buf(d.SP, (size_t)cfg.K * cfg.N, NCCL_UINT64, NCCL_SUM)) return 1;
+    } else {
+      if (refresh_metrics_only()) return 1;
+    }
+    return 0;
+  }
+  int rank_sweep();
+  int refresh_metrics_only();
+
+  int finish_iteration() {
+    k_reduce_partials<T, 256><<<1, 256, 0, stream>>>(d); ++launches;
+    if (allreduce_red()) return 1;
+    k_metrics<T><<<1, 32, 0, stream>>>(d); ++launches;
+    return 0;
+  }
+
+  int init_from_prior(uint32_t have, uint32_t have_prior, double* row) override {
+    CK(cudaSetDevice(cfg.device));
+    const int K = cfg.K, N = cfg.N; const long long KN = (long long)K * N, NG = (long long)N * cfg.G;
+    // which prior-parameter columns to draw: all of them unless supplied without NaN
+    std::vector<int> fl(5 * N, 1);
+    CK(cudaMemcpyAsync(nanflags, fl.data(), sizeof(int) * 5 * N, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    (void)have_prior;
+    for (int side = 0; side < 2; ++side) {
+      const char* names_p[5] = {"Mu_p", "Sigmasq_p", "Lambda_p", "Alpha_p", "Beta_p"};
+      const char* names_e[5] = {"Mu_e", "Sigmasq_e", "Lambda_e", "Alpha_e", "Beta_e"};
+      // (supplied matrices: bit i of have_prior for side p, bit 8+i for side e)
+      for (int w = 0; w < 5; ++w) {
+        const bool supplied = have_prior & (1u << (w + 8 * side));
+        if (!supplied) continue;
+        auto it = st.find(side == 0 ? names_p[w] : names_e[w]);
+        if (it == st.end()) continue;
+        CK(cudaMemsetAsync(nanflags + w * N, 0, sizeof(int) * N, stream));
+        const long long len = side == 0 ? KN : NG;
+        k_nan_cols<T><<<blocks(len, 256), 256, 0, stream>>>((const T*)it->second.p, len, K, N, side, nanflags + w * N);
+        if (allreduce_buf(nanflags + w * N, N, NCCL_INT32, NCCL_MAX)) return 1;
+      }
+      const long long cells = side == 0 ? KN : NG;
+      k_init_prior<T><<<blocks(cells, 128), 128, 0, stream>>>(d, side, nanflags);
+      // reset flags for the next side
+      CK(cudaMemcpyAsync(nanflags, fl.data(), sizeof(int) * 5 * N, cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));
+    }
+    if (cfg.likelihood == BNMF_NORMAL) { if (init_sigmasq_prior()) return 1; }
+    Ctrl c; c.iter = 1; c.converged = 0; c.row = 0; c.ring_pos = 0; c.ring_count = 0;
+    CK(cudaMemcpyAsync(d.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(red_i64, 0, sizeof(long long) * (KN + N), stream));
+    CK(cudaMemsetAsync(d.SE, 0, sizeof(int32_t) * NG, stream));
+    CK(cudaMemsetAsync(work_ctr, 0, sizeof(int) * (n_ktiles + 8), stream));
+    launches = 0;
+    if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (poisson_iteration(1, have, nullptr, nullptr)) return 1; }
+    else { if (mh_iteration(1, have)) return 1; }
+    if (finish_iteration()) return 1;
+    CK(cudaMemcpyAsync(h_metrics, d.metrics, sizeof(double) * MC_COLS, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    if (row) memcpy(row, h_metrics, sizeof(double) * MC_COLS);
+    return 0;
+  }
+  int init_sigmasq_prior();
+
+  int step(int n_iters, int converged, double* metrics, double* P_out, double* A_out) override {
+    CK(cudaSetDevice(cfg.device));
+    if (n_iters < 0) return fail("bnmf_step: n_iters < 0");
+    const int K = cfg.K, N = cfg.N; const long long KN = (long long)K * N;
+    launches = 0;
+    last_z_ms = 0;
+    CK(cudaEventRecord(ev0, stream));
+    int done = 0;
+    std::vector<double> tmp;
+    while (done < n_iters) {
+      const int chunk = std::min(n_iters - done, d.metrics_cap);
+      // ctrl.converged / ctrl.row for this chunk (iter and ring position live on the device)
+      int two[2] = {converged, -1};
+      CK(cudaMemcpyAsync(&d.ctrl->converged, two, sizeof(two), cudaMemcpyHostToDevice, stream));
+      const bool timez = time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
+      if (timez) while ((int)zev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); zev.push_back(e); }
+      for (int i = 0; i < chunk; ++i) {
+        k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); ++launches;
+        if (cfg.likelihood == BNMF_POISSON && !cfg.MH) {
+          if (poisson_iteration(0, 0, timez ? zev[2 * i] : nullptr, timez ? zev[2 * i + 1] : nullptr)) return 1;
+        } else {
+          if (mh_iteration(0, 0)) return 1;
+        }
+        if (finish_iteration()) return 1;
+        if (P_out) CK(cudaMemcpyAsync(P_hist + (long long)i * KN, d.P, sizeof(T) * KN, cudaMemcpyDeviceToDevice, stream));
+        if (A_out) CK(cudaMemcpyAsync(A_hist + (long long)i * N, d.A, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, stream));
+      }
+      CK(cudaMemcpyAsync(h_metrics, d.metrics, sizeof(double) * MC_COLS * chunk, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaGetLastError());
+      if (metrics) memcpy(metrics + (long long)done * MC_COLS, h_metrics, sizeof(double) * MC_COLS * chunk);
+      if (P_out) { if (dev_to_host(P_hist, ST_T, (long long)chunk * KN, P_out + (long long)done * KN)) return 1; }
+      if (A_out) { if (dev_to_host(A_hist, ST_I32, (long long)chunk * N, A_out + (long long)done * N)) return 1; }
+      if (timez) for (int i = 0; i < chunk; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, zev[2 * i], zev[2 * i + 1])); last_z_ms += ms; }
+      done += chunk;
+    }
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaEventSynchronize(ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_total_ms = ms; last_launches = launches;
+    return 0;
+  }
+
+  int ring_count(int* c) override {
+    CK(cudaSetDevice(cfg.device));
+    Ctrl h; CK(cudaMemcpyAsync(&h, d.ctrl, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    *c = h.ring_count;
+    return 0;
+  }
+  int get_sample(const char* name, int ago, double* out, int64_t len) override {
+    CK(cudaSetDevice(cfg.device));
+    if (d.ring_cap <= 0) return fail("bnmf_get_sample: the handle was created with ring_cap = 0");
+    Ctrl h; CK(cudaMemcpyAsync(&h, d.ctrl, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (ago < 0 || ago >= h.ring_count) return fail("bnmf_get_sample: ago = %d outside the %d samples held", ago, h.ring_count);
+    const int slot = ((h.ring_pos - 1 - ago) % d.ring_cap + d.ring_cap) % d.ring_cap;
+    const long long KN = (long long)cfg.K * cfg.N, NG = (long long)cfg.N * cfg.G;
+    if (!strcmp(name, "P")) { if (len != KN) return fail("bnmf_get_sample: P has %lld elements", KN); return dev_to_host(d.ring_P + slot * KN, ST_T, KN, out); }
+    if (!strcmp(name, "E")) { if (len != NG) return fail("bnmf_get_sample: E has %lld elements", NG); return dev_to_host(d.ring_E + slot * NG, ST_T, NG, out); }
+    if (!strcmp(name, "A")) { if (len != cfg.N) return fail("bnmf_get_sample: A has %d elements", cfg.N); return dev_to_host(d.ring_A + (long long)slot * cfg.N, ST_I32, cfg.N, out); }
+    return fail("bnmf_get_sample: the ring holds P, E and A (got '%s')", name);
+  }
+  int get_map(int n_samples, double* P, double* E, double* A, int* n_match) override;
+
+  int timing(double* total, double* z, int64_t* l) override {
+    if (total) *total = last_total_ms;
+    if (z) *z = last_z_ms;
+    if (l) *l = last_launches;
+    return 0;
+  }
+  int sample_z(int iter, double* ms) override {
+    CK(cudaSetDevice(cfg.device));
+    if (!(cfg.likelihood == BNMF_POISSON && !cfg.MH)) return fail("bnmf_sample_z: only the Poisson non-MH model has latent counts");
+    const long long KN = (long long)cfg.K * cfg.N, NG = (long long)cfg.N * cfg.G;
+    CK(cudaMemcpyAsync(&d.ctrl->iter, &iter, sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(d.SP, 0, sizeof(long long) * KN, stream));
+    CK(cudaMemsetAsync(d.SE, 0, sizeof(int32_t) * NG, stream));
+    CK(cudaMemsetAsync(work_ctr, 0, sizeof(int) * (n_ktiles + 8), stream));
+    CK(cudaEventRecord(ev0, stream));
+    if (z_dispatch(false)) return 1;
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaEventSynchronize(ev1));
+    CK(cudaGetLastError());
+    float t = 0; CK(cudaEventElapsedTime(&t, ev0, ev1));
+    if (ms) *ms = t;
+    if (allreduce_buf(d.SP, (size_t)KN, NCCL_UINT64, NCCL_SUM)) return 1;
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+};
+
+// ---- small reductions after a user-supplied P / E -----------------------------------
+template <typename T> static __global__ void k_rowsumE(Dev<T> d) {
+  // one block per n; fixed-point sum is order independent
+  const int n = blockIdx.x;
+  long long s = 0;
+  for (long long g = threadIdx.x; g < d.G; g += blockDim.x) s += llrint((double)d.E[n + (long long)d.N * g] * RS_FX);
+  atomicAdd((unsigned long long*)&d.rowsumE_fx[n], (unsigned long long)s);
+}
+template <typename T> static __global__ void k_colsumP(Dev<T> d) {
+  __shared__ double sc[4];
+  const int n = blockIdx.x;
+  double s = 0;
+  for (int k = threadIdx.x; k < d.K; k += 128) s += (double)d.P[k + (long long)d.K * n];
+  double r = block_sum<128>(s, sc);
+  if (threadIdx.x == 0) d.colsumP[n] = (T)r;
+}
+template <typename T> int Sampler<T>::refresh_rowsumE() {
+  CK(cudaMemsetAsync(d.rowsumE_fx, 0, sizeof(long long) * cfg.N, stream));
+  k_rowsumE<T><<<cfg.N, 256, 0, stream>>>(d);
+  if (allreduce_buf(d.rowsumE_fx, cfg.N, NCCL_INT64, NCCL_SUM)) return 1;
+  CK(cudaStreamSynchronize(stream));
+  return 0;
+}
+template <typename T> int Sampler<T>::refresh_colsumP() {
+  k_colsumP<T><<<cfg.N, 128, 0, stream>>>(d);
+  CK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+#include "bnmf_api_mh.inl"
+#include "bnmf_api_map.inl"
+
+// ---------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+const char* bnmf_last_error(void) { return g_err; }
+
+int bnmf_check_model(int likelihood, int prior, int MH, char* msg, size_t msg_len) {
+  const char* m = nullptr;
+  if (likelihood != BNMF_NORMAL && likelihood != BNMF_POISSON) m = "likelihood must be one of normal, poisson";
+  else if (likelihood == BNMF_NORMAL) {
+    if (!(prior == BNMF_TRUNCNORMAL || prior == BNMF_EXPONENTIAL)) m = "prior must be one of c('truncnormal','exponential') with `likelihood = 'normal'`";
+  } else {
+    if (!(prior == BNMF_GAMMA || prior == BNMF_EXPONENTIAL || prior == BNMF_TRUNCNORMAL)) m = "prior must be one of c('gamma','exponential','truncnormal') with `likelihood = 'poisson'`";
+    else if (prior == BNMF_GAMMA && MH) m = "gamma prior cannot be used in a MH-within-gibbs sampler";
+    else if (prior == BNMF_TRUNCNORMAL && !MH) m = "truncnormal prior can only be used in a MH-within-gibbs sampler";
+  }
+  if (!m) { if (msg && msg_len) msg[0] = 0; return 0; }
+  if (msg && msg_len) snprintf(msg, msg_len, "%s", m);
+  fail("%s", m);
+  return 1;
+}
+
+int bnmf_create(const bnmf_config* cfg, const double* data, bnmf_handle** out) {
+  if (!cfg || !data || !out) return fail("bnmf_create: null argument");
+  *out = nullptr;
+  char msg[256];
+  if (bnmf_check_model(cfg->likelihood, cfg->prior, cfg->MH, msg, sizeof(msg))) return 1;
+  if (cfg->likelihood == BNMF_NORMAL && cfg->MH) return fail("MH applies to the Poisson likelihood only");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return fail("bnmf_create: no CUDA device available (%s); this library has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("bnmf_create: device %d out of range (%d visible)", cfg->device, ndev);
+  if (cfg->precision == BNMF_F64) {
+    auto* s = new Sampler<double>();
+    if (s->create(cfg, data)) { delete s; return 1; }
+    *out = s;
+  } else if (cfg->precision == BNMF_F32) {
+    auto* s = new Sampler<float>();
+    if (s->create(cfg, data)) { delete s; return 1; }
+    *out = s;
+  } else return fail("bnmf_create: precision must be BNMF_F64 or BNMF_F32");
+  return 0;
+}
+void bnmf_destroy(bnmf_handle* h) { delete h; }
+
+#define NEED(h) if (!(h)) return fail("null handle")
+int bnmf_set_hyper(bnmf_handle* h, const char* name, const double* v, int64_t rows, int64_t cols) { NEED(h); return h->set_hyper(name, v, rows, cols); }
+int bnmf_set_state(bnmf_handle* h, const char* name, const double* v, int64_t len) { NEED(h); return h->set_state(name, v, len); }
+int bnmf_get_state(bnmf_handle* h, const char* name, double* out, int64_t len) { NEED(h); return h->get_state(name, out, len); }
+int bnmf_set_temperature_schedule(bnmf_handle* h, const double* t, int64_t n) { NEED(h); return h->set_temps(t, n); }
+int bnmf_init_from_prior(bnmf_handle* h, uint32_t have, uint32_t have_prior, double* row) { NEED(h); return h->init_from_prior(have, have_prior, row); }
+int bnmf_step(bnmf_handle* h, int32_t n, int32_t conv, double* m, double* P, double* A) { NEED(h); return h->step(n, conv, m, P, A); }
+int bnmf_ring_count(bnmf_handle* h, int32_t* c) { NEED(h); return h->ring_count(c); }
+int bnmf_get_sample(bnmf_handle* h, const char* name, int32_t ago, double* out, int64_t len) { NEED(h); return h->get_sample(name, ago, out, len); }
+int bnmf_get_map(bnmf_handle* h, int32_t n, double* P, double* E, double* A, int32_t* nm) { NEED(h); return h->get_map(n, P, E, A, nm); }
+int bnmf_comm_unique_id(char* id128) {
+  if (load_nccl()) return 1;
+  int r = g_nccl.GetUniqueId(id128);
+  if (r) return fail("ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  return 0;
+}
+int bnmf_comm_init(bnmf_handle* h, const char* id, int32_t rank, int32_t world) { NEED(h); return h->comm_init(id, rank, world); }
+int bnmf_timing(bnmf_handle* h, double* t, double* z, int64_t* l) { NEED(h); return h->timing(t, z, l); }
+int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* ms) { NEED(h); return h->sample_z(iter, ms); }
+
+}  // extern "C"

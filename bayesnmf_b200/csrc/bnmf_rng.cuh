@@ -1,0 +1,314 @@
+// Counter-based random draws shared by every bayesnmf_b200 kernel.
+//
+// All randomness in the sampler comes from Philox4x32-10 (Salmon et al., SC'11)
+// keyed by the run seed and addressed by (iteration, purpose, cell, sub-draw), so a
+// draw is a pure function of *what* is being drawn, never of which thread, block,
+// GPU or shard happens to draw it.  The reference (R) uses the global Mersenne
+// Twister stream (stats::rgamma / rexp / rnorm / runif / rmultinom,
+// truncnorm::rtruncnorm, invgamma::rinvgamma, armspp::arms -- see
+// /root/reference/R/sample_Pn.R:14-27,79-85,116-118,243, R/sample_priors.R:219-397,
+// R/sample_params.R:104,164,239,263,279); parity with it is distributional, parity
+// with oracle/ (which restates exactly the arithmetic below in numpy) is
+// draw-for-draw.
+//
+// Everything here is __host__ __device__ so that tests/hostcheck can execute the
+// very same code on the CPU; the product never does.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define BNMF_HD __host__ __device__ __forceinline__
+#else
+#define BNMF_HD inline
+#endif
+
+namespace bnmf {
+
+// ---- draw purposes (low 8 bits of counter word 3) -------------------------------
+enum Purpose : uint32_t {
+  PUR_Z        = 0,   // latent-count picks, cell = k + K*g, sub = pick/4
+  PUR_P        = 1,   // P[k,n] draw (gamma / truncated normal / prior), cell = k + K*n
+  PUR_E        = 2,   // E[n,g] draw, cell = n + N*g
+  PUR_HYP_P1   = 3,   // Beta_p | Lambda_p | Mu_p
+  PUR_HYP_P2   = 4,   // Alpha_p | Sigmasq_p
+  PUR_HYP_E1   = 5,   // Beta_e | Lambda_e | Mu_e
+  PUR_HYP_E2   = 6,   // Alpha_e | Sigmasq_e
+  PUR_MH_P     = 7,   // Metropolis-Hastings accept uniform for P[k,n]
+  PUR_MH_E     = 8,   // Metropolis-Hastings accept uniform for E[n,g]
+  PUR_A        = 9,   // inclusion indicator A_n, cell = n
+  PUR_R        = 10,  // expected rank R, cell = 0
+  PUR_SIGMASQ  = 11,  // sigmasq_g, cell = g
+};
+
+struct U4 { uint32_t x, y, z, w; };
+
+BNMF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// Philox4x32-10.  Counter (c0..c3), key (k0,k1).
+BNMF_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                         uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+// The sampler's addressing convention: key = 64-bit seed; counter =
+// (cell_lo, cell_hi, sub, iter<<8 | purpose).
+struct Stream {
+  uint32_t k0, k1;   // seed
+  uint32_t c3;       // iter<<8 | purpose
+  uint32_t c0, c1;   // cell
+  BNMF_HD U4 at(uint32_t sub) const { return philox4x32_10(c0, c1, sub, c3, k0, k1); }
+};
+
+BNMF_HD Stream make_stream(uint64_t seed, uint32_t iter, uint32_t purpose, uint64_t cell) {
+  Stream s;
+  s.k0 = (uint32_t)seed; s.k1 = (uint32_t)(seed >> 32);
+  s.c3 = (iter << 8) | purpose;
+  s.c0 = (uint32_t)cell; s.c1 = (uint32_t)(cell >> 32);
+  return s;
+}
+
+// ---- uniforms -------------------------------------------------------------------
+// Open interval (0,1): (w + 0.5) * 2^-32 is exact in double.  In float only 24 bits
+// survive, so the float path drops the low byte first (oracle: uniform_bits=24).
+template <typename T> BNMF_HD T u01(uint32_t w);
+template <> BNMF_HD double u01<double>(uint32_t w) {
+  return ((double)w + 0.5) * 2.3283064365386963e-10;  // 2^-32
+}
+template <> BNMF_HD float u01<float>(uint32_t w) {
+  return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-8f;  // 2^-24
+}
+
+// ---- small math helpers kept explicit so that no a*b+c is contracted -----------
+template <typename T> BNMF_HD T tlog(T x) { return log(x); }
+template <typename T> BNMF_HD T texp(T x) { return exp(x); }
+template <typename T> BNMF_HD T tsqrt(T x) { return sqrt(x); }
+template <typename T> BNMF_HD T tlgamma(T x) { return lgamma(x); }
+#if defined(__CUDACC__)
+template <> BNMF_HD float tlog<float>(float x) { return logf(x); }
+template <> BNMF_HD float texp<float>(float x) { return expf(x); }
+template <> BNMF_HD float tsqrt<float>(float x) { return sqrtf(x); }
+template <> BNMF_HD float tlgamma<float>(float x) { return lgammaf(x); }
+#endif
+
+// Standard normal by Box-Muller (cosine branch) from two words.
+template <typename T> BNMF_HD T normal_from(uint32_t w0, uint32_t w1) {
+  T u1 = u01<T>(w0), u2 = u01<T>(w1);
+  T r = tsqrt<T>((T)-2 * tlog<T>(u1));
+  return r * (T)cos((T)6.283185307179586 * u2);
+}
+
+// Exponential(rate): -log(u)/rate.  (stats::rexp, R/sample_Pn.R:21)
+template <typename T> BNMF_HD T exponential_draw(const Stream& s, T rate) {
+  U4 w = s.at(0);
+  return -tlog<T>(u01<T>(w.x)) / rate;
+}
+
+// Normal(mean, sd).  (stats::rnorm, R/sample_priors.R:34,219)
+template <typename T> BNMF_HD T normal_draw(const Stream& s, T mean, T sd) {
+  U4 w = s.at(0);
+  return mean + sd * normal_from<T>(w.x, w.y);
+}
+
+// Gamma(shape, rate) by Marsaglia & Tsang (2000); shape < 1 boosted by U^(1/shape).
+// Attempt t consumes Philox block `sub0 + t`: words (x,y) -> normal, z -> accept
+// uniform, w -> boost uniform.  Result floored at the smallest normal so that a
+// later log() stays finite (R's rgamma can return exactly 0 for tiny shapes).
+// (stats::rgamma(n, shape, rate): R/sample_Pn.R:23-27,116-118, R/sample_priors.R:285-344)
+template <typename T> BNMF_HD T gamma_draw(const Stream& s, T shape, T rate, uint32_t sub0 = 0) {
+  const bool boost = shape < (T)1;
+  const T a = boost ? shape + (T)1 : shape;
+  const T d = a - (T)(1.0 / 3.0);
+  const T c = (T)1 / tsqrt<T>((T)9 * d);
+  T g = d;  // fallback if the attempt cap is ever hit (probability ~ 0)
+  for (uint32_t t = 0; t < 4096u; ++t) {
+    U4 w = s.at(sub0 + t);
+    T x = normal_from<T>(w.x, w.y);
+    T v = (T)1 + c * x;
+    if (v <= (T)0) continue;
+    v = v * v * v;
+    T u = u01<T>(w.z);
+    T x2 = x * x;
+    bool acc = u < (T)1 - (T)0.0331 * (x2 * x2);
+    if (!acc) acc = tlog<T>(u) < (T)0.5 * x2 + d * ((T)1 - v + tlog<T>(v));
+    if (acc) {
+      g = d * v;
+      if (boost) g = g * (T)pow(u01<T>(w.w), (T)1 / shape);
+      break;
+    }
+  }
+  g = g / rate;
+  const T tiny = sizeof(T) == 8 ? (T)DBL_MIN : (T)FLT_MIN;
+  return g < tiny ? tiny : g;
+}
+
+// Normal(mean, sd) truncated to [0, inf).  Every call site of truncnorm::rtruncnorm
+// in the reference has a = 0, b = Inf (R/sample_Pn.R:14-19,59-64,79-85,
+// R/sample_En.R:14-19,59-64,78-84).  With alpha = -mean/sd:
+//   alpha <= 0.45 : plain normal rejection z >= alpha (acceptance >= 0.326)
+//   alpha >  0.45 : Robert (1995) translated-exponential rejection; the result is
+//                   formed as sd*(z-alpha) directly so a mean far below zero does
+//                   not cancel catastrophically.
+// Attempt t consumes Philox block t: (x,y) -> normal or (x -> exp, y -> accept).
+template <typename T> BNMF_HD T truncnorm0_draw(const Stream& s, T mean, T sd) {
+  const T alpha = -mean / sd;
+  if (alpha <= (T)0.45) {
+    T z = alpha;
+    for (uint32_t t = 0; t < 4096u; ++t) {
+      U4 w = s.at(t);
+      T zz = normal_from<T>(w.x, w.y);
+      if (zz >= alpha) { z = zz; break; }
+    }
+    T x = mean + sd * z;
+    return x < (T)0 ? (T)0 : x;
+  }
+  const T lam = (T)0.5 * (alpha + tsqrt<T>(alpha * alpha + (T)4));
+  T e = (T)0;
+  for (uint32_t t = 0; t < 4096u; ++t) {
+    U4 w = s.at(t);
+    T ee = -tlog<T>(u01<T>(w.x)) / lam;   // z - alpha
+    T dz = (alpha + ee) - lam;
+    if (tlog<T>(u01<T>(w.y)) <= (T)-0.5 * (dz * dz)) { e = ee; break; }
+  }
+  return sd * e;
+}
+
+// ---- digamma / trigamma (recurrence to x >= 6, then asymptotic series) ----------
+template <typename T> BNMF_HD T digamma(T x) {
+  T r = (T)0;
+  while (x < (T)6) { r = r - (T)1 / x; x = x + (T)1; }
+  T f = (T)1 / (x * x);
+  T t = f * ((T)(-1.0 / 12.0) + f * ((T)(1.0 / 120.0) + f * ((T)(-1.0 / 252.0) +
+        f * ((T)(1.0 / 240.0) + f * (T)(-1.0 / 132.0)))));
+  return r + tlog<T>(x) - (T)0.5 / x + t;
+}
+template <typename T> BNMF_HD T trigamma(T x) {
+  T r = (T)0;
+  while (x < (T)6) { r = r + (T)1 / (x * x); x = x + (T)1; }
+  T f = (T)1 / (x * x);
+  T t = (T)1 / x + (T)0.5 * f +
+        (f / x) * ((T)(1.0 / 6.0) + f * ((T)(-1.0 / 30.0) + f * ((T)(1.0 / 42.0) +
+        f * (T)(-1.0 / 30.0))));
+  return r + t;
+}
+
+// ---- shape parameter of the Gamma prior --------------------------------------
+// The reference draws Alpha[.] with armspp::arms(n_samples = 1, log_pdf, 1e-3, 1e4)
+// (R/sample_priors.R:356-397) from
+//   log f(x) = (C-1) log x - D x + x log(Beta) + (x-1) log(X) - lgamma(x)
+//            = cm1 log x - b x - lgamma(x) + const,   b = D - log(Beta) - log(X).
+// f'' = -(C-1)/x^2 - trigamma(x) < -C/x^2 < 0, so the target is log-concave for
+// every C > 0 and ARMS degenerates to exact adaptive rejection sampling.  We draw
+// exactly from the same density with a fixed three-tangent envelope (tangents at
+// mode-s, mode, mode+s, s = Laplace sd), i.e. non-adaptive ARS.  Any choice of
+// tangent points gives a valid envelope; only the acceptance rate depends on them.
+struct AlphaTarget { double cm1, b; };
+BNMF_HD double alpha_h(const AlphaTarget& t, double x) { return t.cm1 * log(x) - t.b * x - lgamma(x); }
+BNMF_HD double alpha_hp(const AlphaTarget& t, double x) { return t.cm1 / x - t.b - digamma<double>(x); }
+BNMF_HD double alpha_hpp(const AlphaTarget& t, double x) { return -t.cm1 / (x * x) - trigamma<double>(x); }
+
+// integral of exp(s*(x - x0)) over [a, b], a <= b, computed stably.
+BNMF_HD double seg_mass(double s, double a, double b, double x0) {
+  double w = b - a;
+  double sw = s * w;
+  double base = exp(s * (a - x0));
+  if (fabs(sw) < 1e-8) return base * w * (1.0 + 0.5 * sw);
+  return base * expm1(sw) / s;
+}
+// inverse of the above: x in [a,b] with partial mass fraction q in (0,1).
+BNMF_HD double seg_inv(double s, double a, double b, double q) {
+  double w = b - a;
+  double sw = s * w;
+  if (fabs(sw) < 1e-8) return a + q * w;
+  return a + log1p(q * expm1(sw)) / s;
+}
+
+BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, double X) {
+  const double LO = 1e-3, HI = 1e4;
+  AlphaTarget t; t.cm1 = C - 1.0; t.b = D - log(beta) - log(X);
+  // --- mode by safeguarded Newton on h' (strictly decreasing), 16 fixed steps ---
+  double m;
+  if (alpha_hp(t, LO) <= 0.0) m = LO;
+  else if (alpha_hp(t, HI) >= 0.0) m = HI;
+  else {
+    double a = LO, b = HI;
+    double x = C > 1.0 ? C : 1.0;   // crude start
+    if (x >= HI) x = 0.5 * HI;
+    for (int it = 0; it < 16; ++it) {
+      double f = alpha_hp(t, x);
+      if (f > 0.0) a = x; else b = x;
+      double xn = x - f / alpha_hpp(t, x);
+      if (fabs(xn - x) <= 1e-10 * x) xn = x;            // converged: freeze
+      else if (!(xn > a && xn < b)) xn = sqrt(a * b);   // safeguard: geometric bisection
+      x = xn;
+    }
+    m = x;
+  }
+  double s = 1.0 / sqrt(-alpha_hpp(t, m));
+  // --- three tangent points inside (0, inf), strictly increasing ---
+  double xs[3];
+  xs[1] = m;
+  xs[0] = (m - s > 0.5 * m) ? m - s : 0.5 * m;
+  xs[2] = m + s;
+  if (m <= LO) { xs[0] = LO; xs[1] = LO + s; xs[2] = LO + 2.0 * s; }
+  if (m >= HI) { xs[2] = HI; xs[1] = HI - s; xs[0] = HI - 2.0 * s; if (xs[0] < 0.5 * HI) { xs[0] = 0.5 * HI; xs[1] = 0.75 * HI; } }
+  double hv[3], sl[3];
+  for (int j = 0; j < 3; ++j) { hv[j] = alpha_h(t, xs[j]); sl[j] = alpha_hp(t, xs[j]); }
+  // --- segment boundaries: tangent intersections, clipped to [LO, HI] ---
+  double z[4];
+  z[0] = LO; z[3] = HI;
+  for (int j = 0; j < 2; ++j) {
+    double den = sl[j] - sl[j + 1];
+    double zz = (hv[j + 1] - hv[j] + sl[j] * xs[j] - sl[j + 1] * xs[j + 1]) / den;
+    if (!(zz >= xs[j])) zz = xs[j];
+    if (!(zz <= xs[j + 1])) zz = xs[j + 1];
+    if (zz < LO) zz = LO;
+    if (zz > HI) zz = HI;
+    z[j + 1] = zz;
+  }
+  double hmax = hv[0];
+  if (hv[1] > hmax) hmax = hv[1];
+  if (hv[2] > hmax) hmax = hv[2];
+  double mass[3], tot = 0.0;
+  for (int j = 0; j < 3; ++j) {
+    mass[j] = (z[j + 1] > z[j]) ? exp(hv[j] - hmax) * seg_mass(sl[j], z[j], z[j + 1], xs[j]) : 0.0;
+    tot += mass[j];
+  }
+  double x = m;
+  for (uint32_t a = 0; a < 4096u; ++a) {
+    U4 w = st.at(a);
+    double r = u01<double>(w.x) * tot;
+    int j = 0;
+    if (r >= mass[0]) { r -= mass[0]; j = 1; if (r >= mass[1]) { r -= mass[1]; j = 2; } }
+    if (!(mass[j] > 0.0)) continue;
+    double q = r / mass[j];
+    if (q >= 1.0) q = 1.0 - 1e-16;
+    double xc = seg_inv(sl[j], z[j], z[j + 1], q);
+    if (xc < z[j]) xc = z[j];
+    if (xc > z[j + 1]) xc = z[j + 1];
+    double env = hv[j] + sl[j] * (xc - xs[j]);
+    if (log(u01<double>(w.y)) <= alpha_h(t, xc) - env) { x = xc; break; }
+  }
+  return x;
+}
+
+}  // namespace bnmf

@@ -1,0 +1,143 @@
+/* bnmf.h -- C ABI of the B200-native Gibbs sampler behind jennalandy/bayesNMF.
+ *
+ * The reference is pure R and has no FFI; the seam this library replaces is the
+ * private-method layer of the R6 class `bayesNMF_sampler`
+ *     private$sample_prior_params()   R/bayesNMF_sampler.R:575-577 -> R/sample_priors.R:150-200
+ *     private$sample_params()         R/bayesNMF_sampler.R:598-600 -> R/sample_params.R:51-89
+ *     private$record_sample()         R/bayesNMF_sampler.R:651-672
+ *     private$update_sample_metrics() R/bayesNMF_sampler.R:699-704 -> R/utils.R:339-348, :412-455
+ * as called from initialize() (R/bayesNMF_sampler.R:232-257) and from the loop body
+ * of run_gibbs_sampler() (R/bayesNMF_sampler.R:268-285, :337-348).
+ *
+ * Conventions (what an R `.Call` veneer, or ctypes, relies on):
+ *   - plain C, no C++/torch types; every function returns 0 on success, non-zero on
+ *     error, never throws or longjmps; bnmf_last_error() gives the message;
+ *   - all host buffers are caller-owned, column-major, double (R's REALSXP) unless
+ *     stated; the library copies in/out and never keeps a host pointer;
+ *   - one host thread per handle; a handle is bound to one CUDA device;
+ *   - indices are 0-based here; iteration numbers are the reference's (1 = the
+ *     prior draw, R/bayesNMF_sampler.R:39-43).
+ */
+#ifndef BNMF_H
+#define BNMF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bnmf_handle bnmf_handle;
+
+enum { BNMF_POISSON = 0, BNMF_NORMAL = 1 };                         /* specs$likelihood */
+enum { BNMF_TRUNCNORMAL = 0, BNMF_EXPONENTIAL = 1, BNMF_GAMMA = 2 };/* specs$prior      */
+enum { BNMF_SBFI = 0, BNMF_BFI = 1, BNMF_BIC = 2 };                 /* specs$rank_method*/
+enum { BNMF_F64 = 0, BNMF_F32 = 1 };                                /* state precision  */
+
+/* columns of one sample_metrics row (R/utils.R:435-452, :341-342) */
+enum {
+  BNMF_MC_ITER = 0, BNMF_MC_RMSE, BNMF_MC_KL, BNMF_MC_LOGLIK, BNMF_MC_LOGPOST,
+  BNMF_MC_NPARAMS, BNMF_MC_BIC, BNMF_MC_RANK, BNMF_MC_TEMP,
+  BNMF_MC_PACC, BNMF_MC_EACC, BNMF_MC_COLS
+};
+
+/* bits of the `have` mask of bnmf_init_from_prior = names(init_params) of
+ * R/bayesNMF_sampler.R:241 (sample_params(skip = names(init_params), from_prior = TRUE)) */
+enum { BNMF_HAVE_P = 1, BNMF_HAVE_E = 2, BNMF_HAVE_A = 4, BNMF_HAVE_Z = 8, BNMF_HAVE_SIGMASQ = 16 };
+
+typedef struct bnmf_config {
+  int32_t K;             /* nrow(data)                        R/bayesNMF_sampler.R:142 */
+  int32_t N;             /* max(rank)                         R/bayesNMF_sampler.R:143 */
+  int64_t G;             /* ncol(data) held by THIS handle (its shard)                */
+  int64_t G_total;       /* ncol(data) of the whole problem (== G when not sharded)   */
+  int64_t g0;            /* global index of this shard's first column                 */
+  int32_t likelihood;    /* BNMF_POISSON | BNMF_NORMAL                                */
+  int32_t prior;         /* BNMF_TRUNCNORMAL | BNMF_EXPONENTIAL | BNMF_GAMMA          */
+  int32_t MH;            /* specs$MH                                                  */
+  int32_t learning_rank; /* specs$learning_rank  (length(rank) > 1)                   */
+  int32_t rank_method;   /* BNMF_SBFI | BNMF_BFI   (BIC fans out on the host)         */
+  int32_t precision;     /* BNMF_F64 (parity) | BNMF_F32                              */
+  int32_t device;        /* CUDA device ordinal                                       */
+  int32_t ring_cap;      /* samples kept on the device = MAP_over (0: keep none)      */
+  uint64_t seed;         /* Philox key                                                */
+} bnmf_config;
+
+/* Check that (likelihood, prior, MH) is a model the reference accepts
+ * (check_model, R/bayesNMF_sampler.R:623-645).  Needs no GPU.  0 = valid. */
+int bnmf_check_model(int likelihood, int prior, int MH, char* msg, size_t msg_len);
+
+/* Create a sampler: upload `data` (K x G column-major doubles; must be integer-valued
+ * and >= 0 for the Poisson likelihood) and allocate all state in HBM.
+ * Called where initialize() stores self$data/self$dims (R/bayesNMF_sampler.R:140-158). */
+int bnmf_create(const bnmf_config* cfg, const double* data, bnmf_handle** out);
+void bnmf_destroy(bnmf_handle* h);
+/* message of the last failing call on this thread */
+const char* bnmf_last_error(void);
+
+/* Hyperprior parameters, scalar (rows = cols = 1) or full matrix, as filled by
+ * fill_hyperprior_params_ (R/setup.R:15-88).  Names: "A_p","B_p","C_p","D_p","M_p",
+ * "S_p" (K x N) and "A_e",...,"S_e" (N x G).  Matrices for *_e cover this shard. */
+int bnmf_set_hyper(bnmf_handle* h, const char* name, const double* v, int64_t rows, int64_t cols);
+
+/* Current state, by the reference's names.  Parameters: "P" (K x N), "E" (N x G),
+ * "A" (1 x N), "R" (1), "sigmasq" (G).  Prior parameters: "Mu_p","Sigmasq_p",
+ * "Lambda_p","Alpha_p","Beta_p" (K x N); "Mu_e",...,"Beta_e" (N x G); "Alpha","Beta"
+ * (G, sigmasq prior).  Statistics replacing Z: "SP" = sum_g Z (K x N), "SE" = sum_k Z
+ * (N x G).  "P_acceptance_rate" (K x N), "E_acceptance_rate" (N x G), "Mhat" (K x G).
+ * NaN entries in a prior parameter mean "draw this column from the hyperprior"
+ * (R/sample_priors.R:33-60). */
+int bnmf_set_state(bnmf_handle* h, const char* name, const double* v, int64_t len);
+int bnmf_get_state(bnmf_handle* h, const char* name, double* out, int64_t len);
+
+/* temperature_schedule (R/utils.R:307-332), indexed by iteration (entry 0 = iter 1). */
+int bnmf_set_temperature_schedule(bnmf_handle* h, const double* temps, int64_t n);
+
+/* Iteration 1: init_prior_params_ + sample_params_(from_prior = TRUE) + record_sample
+ * + update_sample_metrics (R/bayesNMF_sampler.R:232-257).  States named in `have`
+ * were supplied with bnmf_set_state and are kept verbatim; prior parameters that
+ * were supplied are kept except for NaN columns.  metrics_row: BNMF_MC_COLS doubles. */
+int bnmf_init_from_prior(bnmf_handle* h, uint32_t have, uint32_t have_prior, double* metrics_row);
+
+/* Advance n_iters full Gibbs iterations on the device (prior parameters -> P -> E
+ * -> R,A -> Z -> sigmasq -> record -> metrics; R/bayesNMF_sampler.R:273-285).
+ *   converged   state$converged: real Metropolis-Hastings accept step on/off
+ *               (R/sample_Pn.R:201-204, R/sample_En.R:198-201)
+ *   metrics_out n_iters x BNMF_MC_COLS, row-major (one sample_metrics row per iter)
+ *   P_out       NULL or K x N x n_iters   (samples$P of these iterations)
+ *   A_out       NULL or N x n_iters       (samples$A)
+ * Other samples stay in the device ring (bnmf_get_samples). */
+int bnmf_step(bnmf_handle* h, int32_t n_iters, int32_t converged,
+              double* metrics_out, double* P_out, double* A_out);
+
+/* Sample ring (record_sample / update_list, R/bayesNMF_sampler.R:651-672,
+ * R/helpers.R:111-119): the last `ring_cap` samples of "P", "E", "A".
+ * `ago` = 0 is the newest sample. */
+int bnmf_ring_count(bnmf_handle* h, int32_t* count);
+int bnmf_get_sample(bnmf_handle* h, const char* name, int32_t ago, double* out, int64_t len);
+
+/* get_MAP_ on the device (R/utils.R:194-288): over the newest `n_samples` ring
+ * samples, keep those whose A equals the modal A, renormalise (R/helpers.R:35-49)
+ * and average.  P_map K x N, E_map N x G, A_map N; n_match = samples averaged. */
+int bnmf_get_map(bnmf_handle* h, int32_t n_samples, double* P_map, double* E_map,
+                 double* A_map, int32_t* n_match);
+
+/* Cross-shard reduction for genome-sharded runs (one process per GPU): each rank
+ * creates its shard handle, rank 0 makes an id, every rank joins.  Afterwards
+ * bnmf_step sums SP, rowSums(E) and the metric partials over ranks with NCCL. */
+int bnmf_comm_unique_id(char* id128);
+int bnmf_comm_init(bnmf_handle* h, const char* id128, int32_t rank, int32_t world);
+
+/* Device timing of the last bnmf_step call (CUDA events): total and the share of
+ * the latent-count kernel, both in milliseconds; launches = kernels launched. */
+int bnmf_timing(bnmf_handle* h, double* total_ms, double* zstat_ms, int64_t* launches);
+
+/* Stand-alone entry for the fused latent-count + sufficient-statistic kernel on the
+ * handle's current P, E, A at iteration `iter` (parity tests, roofline timing).
+ * Overwrites SP / SE. */
+int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNMF_H */

@@ -1,0 +1,101 @@
+"""GPU parity tests of the Poisson (non-MH) path against the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from tests.util import synth_counts
+
+pytestmark = pytest.mark.gpu
+
+
+def _handle(M, N, prior="gamma", seed=3, **kw):
+    from bayesnmf_b200 import Handle
+    return Handle(M, N, likelihood="poisson", prior=prior, MH=False, seed=seed, **kw)
+
+
+@pytest.mark.parametrize("K,G,N,mu", [(96, 64, 5, 4000.0), (96, 100, 20, 4000.0), (130, 77, 7, 300.0),
+                                      (33, 1, 3, 50.0), (96, 300, 40, 100.0), (200, 45, 64, 2000.0)])
+def test_zstat_bit_exact(built_lib, K, G, N, mu):
+    """Latent-count margins are bit-exact under shared Philox draws (north star level 1)."""
+    from oracle.gibbs import sample_Z_stats
+    rng = np.random.default_rng(K + G + N)
+    M, _, _ = synth_counts(K, G, N, mu, seed=1)
+    P = rng.gamma(1.0, 0.02, size=(K, N))
+    E = rng.gamma(1.0, mu / N, size=(N, G))
+    A = np.ones(N)
+    if N > 2:
+        A[1] = 0                      # an excluded signature: its Z must be 0
+    if G > 3:
+        E[:, 2] = 0.0                 # all-zero probabilities: the whole column of Z is 0
+    M[0, 0] = 0
+    h = _handle(M, N)
+    h.set_state("P", P); h.set_state("E", E); h.set_state("A", A)
+    ms = h.sample_z(7)
+    SP, SE = h.get_state("SP"), h.get_state("SE")
+    oSP, oSE, Z = sample_Z_stats(M, P, A, E, seed=3, it=7, return_Z=True)
+    assert np.array_equal(SP, oSP)
+    assert np.array_equal(SE, oSE)
+    # invariants of R/sample_params.R:253-265
+    Mhat = (P * A) @ E
+    assert np.array_equal(Z.sum(axis=1)[Mhat > 0], M[Mhat > 0])
+    assert SP.sum() == SE.sum() == M[Mhat > 0].sum()
+    if N > 2:
+        assert SP[:, 1].sum() == 0 and SE[1].sum() == 0
+    assert ms > 0
+
+
+def test_zstat_changes_with_iteration_and_seed(built_lib):
+    M, P, E = synth_counts(96, 40, 5, 500.0, seed=2)
+    h = _handle(M, 5, seed=11)
+    h.set_state("P", P); h.set_state("E", E); h.set_state("A", np.ones(5))
+    h.sample_z(2); a = h.get_state("SP")
+    h.sample_z(3); b = h.get_state("SP")
+    h.sample_z(2); c = h.get_state("SP")
+    assert np.array_equal(a, c) and not np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("prior", ["gamma", "exponential"])
+@pytest.mark.parametrize("K,G,N", [(96, 64, 5), (50, 37, 3)])
+def test_iteration_parity(built_lib, prior, K, G, N):
+    """Conditional draws, prior parameters and metrics within 1e-6 relative (fp64),
+    latent-count margins bit-exact, over several full Gibbs iterations."""
+    from oracle.gibbs import OracleSampler
+    M, _, _ = synth_counts(K, G, N, 2000.0, seed=5)
+    o = OracleSampler(M, N, "poisson", prior, MH=False, seed=9)
+    h = _handle(M, N, prior=prior, seed=9)
+    for k, v in o.hyper.items():
+        h.set_hyper(k, v[0, 0])
+    row = h.init_from_prior()
+    names = ["P", "E"] + (["Alpha_p", "Beta_p", "Alpha_e", "Beta_e"] if prior == "gamma" else ["Lambda_p", "Lambda_e"])
+
+    def check(tag):
+        for nm in names:
+            ref = o.params[nm] if nm in o.params else o.prior_params[nm]
+            np.testing.assert_allclose(h.get_state(nm), ref, rtol=1e-6, atol=1e-300, err_msg=f"{tag} {nm}")
+        assert np.array_equal(h.get_state("SP"), o.SP), tag
+        assert np.array_equal(h.get_state("SE"), o.SE), tag
+
+    check("init")
+    om = o.metrics[0]
+    for key in ("RMSE", "KL", "loglikelihood", "logposterior", "n_params", "BIC", "rank"):
+        np.testing.assert_allclose(row[key], om[key], rtol=1e-6, err_msg=f"init {key}")
+    for it in range(4):
+        om = o.step()
+        met = h.step(1)["metrics"][0]
+        check(f"iter {o.iter}")
+        from bayesnmf_b200._lib import METRIC_NAMES
+        got = dict(zip(METRIC_NAMES, met))
+        assert got["iter"] == o.iter
+        for key in ("RMSE", "KL", "loglikelihood", "logposterior", "n_params", "BIC", "rank", "temp"):
+            np.testing.assert_allclose(got[key], om[key], rtol=1e-6, err_msg=f"iter {o.iter} {key}")
+
+
+def test_step_chunks_equal_single_steps(built_lib):
+    """bnmf_step(n) == n x bnmf_step(1): the draw streams depend on the iteration only."""
+    M, _, _ = synth_counts(96, 50, 4, 1000.0, seed=7)
+    a = _handle(M, 4, seed=21); a.init_from_prior()
+    b = _handle(M, 4, seed=21); b.init_from_prior()
+    ra = a.step(6, want_P=True)
+    rows = [b.step(1, want_P=True) for _ in range(6)]
+    np.testing.assert_array_equal(ra["metrics"], np.concatenate([r["metrics"] for r in rows]))
+    np.testing.assert_array_equal(ra["P"], np.concatenate([r["P"] for r in rows]))
+    np.testing.assert_array_equal(a.get_state("E"), b.get_state("E"))
