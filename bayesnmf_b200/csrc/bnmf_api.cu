@@ -212,8 +212,15 @@ struct Sampler : bnmf_handle {
     if (cfg.MH) { if (reg("P_acceptance_rate", &d.P_acc, KN) || reg("E_acceptance_rate", &d.E_acc, NG)) return 1; }
     if (cfg.MH || cfg.likelihood == BNMF_NORMAL || cfg.learning_rank) { if (reg("Mhat", &d.Mhat, KG)) return 1; }
 
-    // work decomposition of the column kernels
+    // work decomposition of the column kernels: the k-tile is the largest multiple of 32
+    // rows (<= 128) whose P tile + accumulators fit next to the per-thread CDF/histogram
+    NP = ((N + 3) / 4) * 4; if (NP > 32) NP = ((N + 7) / 8) * 8;
+    const int np2 = NP <= 4 ? 4 : NP <= 8 ? 8 : NP <= 16 ? 16 : NP <= 32 ? 32 : 64;
+    const size_t z_fixed = (size_t)np2 * ZT * sizeof(T) + (size_t)NP * ZT * sizeof(int);
+    const size_t z_budget = NP <= 32 ? (size_t)112 * 1024 : (size_t)226 * 1024;
     KT = ((K + 31) / 32) * 32; if (KT > 128) KT = 128;
+    while (KT > 32 && z_fixed + (size_t)KT * (NP * sizeof(T) + N * sizeof(int)) > z_budget) KT -= 32;
+    z_smem = z_fixed + (size_t)KT * (NP * sizeof(T) + N * sizeof(int));
     n_ktiles = (K + KT - 1) / KT;
     const int cts = (int)((G + 31) / 32);
     d.n_zitems = cts * n_ktiles * ((KT + 31) / 32);
@@ -258,13 +265,6 @@ struct Sampler : bnmf_handle {
       k_cvt_in<T><<<blocks(KG, 256), 256, 0, stream>>>(stage, mr, KG);
       d.Mr = mr;
       st["data"] = StEntry{mr, KG, ST_T};
-    }
-    // kernel configuration of k_zstat
-    NP = ((N + 3) / 4) * 4; if (NP > 32) NP = ((N + 7) / 8) * 8;
-    {
-      int np2 = NP <= 4 ? 4 : NP <= 8 ? 8 : NP <= 16 ? 16 : NP <= 32 ? 32 : 64;
-      z_smem = (size_t)KT * NP * sizeof(T) + (size_t)np2 * ZT * sizeof(T) + (size_t)NP * ZT * sizeof(int) +
-               (size_t)KT * N * sizeof(int);
     }
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (z_config()) return 1; }
     if (mh_setup()) return 1;

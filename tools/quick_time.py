@@ -10,6 +10,9 @@ def run(K, G, N, mu, iters=20, prior="gamma"):
     t0 = time.time()
     h = Handle(M, N, likelihood="poisson", prior=prior, MH=False, seed=1, ring_cap=0)
     t1 = time.time()
+    from oracle.gibbs import default_hyperprior_params
+    for k, v in default_hyperprior_params(prior, M.mean(), N).items():
+        h.set_hyper(k[0].upper() + k[1:], v)
     h.init_from_prior()
     h.step(5)
     zs = [h.sample_z(100 + i) for i in range(5)]
