@@ -1,2 +1,2 @@
 """bayesnmf_b200 -- B200-native Gibbs sampler behind the bayesNMF sampler API."""
-from ._lib import BnmfError, Handle  # noqa: F401
+from ._lib import BnmfError, Handle, comm_unique_id  # noqa: F401

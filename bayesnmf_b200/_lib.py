@@ -68,7 +68,8 @@ def lib():
     L.bnmf_get_map.argtypes = [vp, i32, dp, dp, dp, ctypes.POINTER(i32)]
     L.bnmf_comm_unique_id.argtypes = [ctypes.c_char_p]
     L.bnmf_comm_init.argtypes = [vp, ctypes.c_char_p, i32, i32]
-    L.bnmf_timing.argtypes = [vp, dp, dp, ctypes.POINTER(i64)]
+    L.bnmf_timing.argtypes = [vp, dp, dp, dp, ctypes.POINTER(i64)]
+    L.bnmf_set_l2_flush.argtypes = [vp, ctypes.c_size_t]
     L.bnmf_sample_z.argtypes = [vp, i32, dp]
     _lib = L
     return L
@@ -77,7 +78,7 @@ def lib():
 EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
            "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
            "bnmf_step", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_comm_unique_id",
-           "bnmf_comm_init", "bnmf_timing", "bnmf_sample_z"]
+           "bnmf_comm_init", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z"]
 
 
 def _dp(a):
@@ -200,9 +201,12 @@ class Handle:
         self._ck(lib().bnmf_comm_init(self._h, uid, int(rank), int(world)))
 
     def timing(self):
-        t = ctypes.c_double(); z = ctypes.c_double(); l = ctypes.c_int64()
-        self._ck(lib().bnmf_timing(self._h, ctypes.byref(t), ctypes.byref(z), ctypes.byref(l)))
-        return {"total_ms": t.value, "zstat_ms": z.value, "launches": l.value}
+        t = ctypes.c_double(); i = ctypes.c_double(); z = ctypes.c_double(); l = ctypes.c_int64()
+        self._ck(lib().bnmf_timing(self._h, ctypes.byref(t), ctypes.byref(i), ctypes.byref(z), ctypes.byref(l)))
+        return {"total_ms": t.value, "iter_ms": i.value, "zstat_ms": z.value, "launches": l.value}
+
+    def set_l2_flush(self, nbytes):
+        self._ck(lib().bnmf_set_l2_flush(self._h, int(nbytes)))
 
     def sample_z(self, it):
         ms = ctypes.c_double()

@@ -73,7 +73,8 @@ struct bnmf_handle {
   virtual int get_sample(const char* name, int ago, double* out, int64_t len) = 0;
   virtual int get_map(int n_samples, double* P, double* E, double* A, int* n_match) = 0;
   virtual int comm_init(const char* id, int rank, int world) = 0;
-  virtual int timing(double* total, double* z, int64_t* launches) = 0;
+  virtual int timing(double* total, double* iter, double* z, int64_t* launches) = 0;
+  virtual int set_l2_flush(size_t bytes) = 0;
   virtual int sample_z(int iter, double* ms) = 0;
 };
 
@@ -129,7 +130,9 @@ struct Sampler : bnmf_handle {
   void* comm = nullptr; int world = 1, rank = 0;
   long long* red_i64 = nullptr;                           // [K*N + N] packed int64 reduction buffer
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::vector<cudaEvent_t> zev;
+  std::vector<cudaEvent_t> zev, iev;
+  void* flush_buf = nullptr; size_t flush_bytes = 0;
+  double last_iter_ms = 0;
   bool time_z = true;
   double last_total_ms = 0, last_z_ms = 0; int64_t last_launches = 0;
   bool have_temps = false;
@@ -140,6 +143,8 @@ struct Sampler : bnmf_handle {
     for (void* p : allocs) cudaFree(p);
     if (h_metrics) cudaFreeHost(h_metrics);
     for (auto e : zev) cudaEventDestroy(e);
+    for (auto e : iev) cudaEventDestroy(e);
+    if (flush_buf) cudaFree(flush_buf);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -494,7 +499,7 @@ struct Sampler : bnmf_handle {
     if (n_iters < 0) return fail("bnmf_step: n_iters < 0");
     const int K = cfg.K, N = cfg.N; const long long KN = (long long)K * N;
     launches = 0;
-    last_z_ms = 0;
+    last_z_ms = 0; last_iter_ms = 0;
     CK(cudaEventRecord(ev0, stream));
     int done = 0;
     std::vector<double> tmp;
@@ -505,7 +510,10 @@ struct Sampler : bnmf_handle {
       CK(cudaMemcpyAsync(&d.ctrl->converged, two, sizeof(two), cudaMemcpyHostToDevice, stream));
       const bool timez = time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
       if (timez) while ((int)zev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); zev.push_back(e); }
+      while ((int)iev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); iev.push_back(e); }
       for (int i = 0; i < chunk; ++i) {
+        if (flush_bytes) CK(cudaMemsetAsync(flush_buf, i & 0xff, flush_bytes, stream));
+        CK(cudaEventRecord(iev[2 * i], stream));
         k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); ++launches;
         if (cfg.likelihood == BNMF_POISSON && !cfg.MH) {
           if (poisson_iteration(0, 0, timez ? zev[2 * i] : nullptr, timez ? zev[2 * i + 1] : nullptr)) return 1;
@@ -513,6 +521,7 @@ struct Sampler : bnmf_handle {
           if (mh_iteration(0, 0)) return 1;
         }
         if (finish_iteration()) return 1;
+        CK(cudaEventRecord(iev[2 * i + 1], stream));
         if (P_out) CK(cudaMemcpyAsync(P_hist + (long long)i * KN, d.P, sizeof(T) * KN, cudaMemcpyDeviceToDevice, stream));
         if (A_out) CK(cudaMemcpyAsync(A_hist + (long long)i * N, d.A, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, stream));
       }
@@ -523,6 +532,7 @@ struct Sampler : bnmf_handle {
       if (P_out) { if (dev_to_host(P_hist, ST_T, (long long)chunk * KN, P_out + (long long)done * KN)) return 1; }
       if (A_out) { if (dev_to_host(A_hist, ST_I32, (long long)chunk * N, A_out + (long long)done * N)) return 1; }
       if (timez) for (int i = 0; i < chunk; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, zev[2 * i], zev[2 * i + 1])); last_z_ms += ms; }
+      for (int i = 0; i < chunk; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, iev[2 * i], iev[2 * i + 1])); last_iter_ms += ms; }
       done += chunk;
     }
     CK(cudaEventRecord(ev1, stream));
@@ -554,8 +564,17 @@ struct Sampler : bnmf_handle {
   }
   int get_map(int n_samples, double* P, double* E, double* A, int* n_match) override;
 
-  int timing(double* total, double* z, int64_t* l) override {
+  int set_l2_flush(size_t bytes) override {
+    CK(cudaSetDevice(cfg.device));
+    CK(cudaStreamSynchronize(stream));
+    if (flush_buf) { CK(cudaFree(flush_buf)); flush_buf = nullptr; }
+    flush_bytes = 0;
+    if (bytes) { CK(cudaMalloc(&flush_buf, bytes)); flush_bytes = bytes; }
+    return 0;
+  }
+  int timing(double* total, double* iter, double* z, int64_t* l) override {
     if (total) *total = last_total_ms;
+    if (iter) *iter = last_iter_ms;
     if (z) *z = last_z_ms;
     if (l) *l = last_launches;
     return 0;
@@ -677,7 +696,8 @@ int bnmf_comm_unique_id(char* id128) {
   return 0;
 }
 int bnmf_comm_init(bnmf_handle* h, const char* id, int32_t rank, int32_t world) { NEED(h); return h->comm_init(id, rank, world); }
-int bnmf_timing(bnmf_handle* h, double* t, double* z, int64_t* l) { NEED(h); return h->timing(t, z, l); }
+int bnmf_timing(bnmf_handle* h, double* t, double* it, double* z, int64_t* l) { NEED(h); return h->timing(t, it, z, l); }
+int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes) { NEED(h); return h->set_l2_flush(bytes); }
 int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* ms) { NEED(h); return h->sample_z(iter, ms); }
 
 }  // extern "C"

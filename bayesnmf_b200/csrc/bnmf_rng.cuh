@@ -226,19 +226,21 @@ BNMF_HD double alpha_h(const AlphaTarget& t, double x) { return t.cm1 * log(x) -
 BNMF_HD double alpha_hp(const AlphaTarget& t, double x) { return t.cm1 / x - t.b - digamma<double>(x); }
 BNMF_HD double alpha_hpp(const AlphaTarget& t, double x) { return -t.cm1 / (x * x) - trigamma<double>(x); }
 
-// integral of exp(s*(x - x0)) over [a, b], a <= b, computed stably.
+// integral of exp(s*(x - x0)) over [a, b], a <= b, anchored at the end with the larger
+// exponent so that expm1 only ever sees a non-positive argument (no overflow).
 BNMF_HD double seg_mass(double s, double a, double b, double x0) {
   double w = b - a;
   double sw = s * w;
-  double base = exp(s * (a - x0));
-  if (fabs(sw) < 1e-8) return base * w * (1.0 + 0.5 * sw);
-  return base * expm1(sw) / s;
+  if (fabs(sw) < 1e-8) return exp(s * (a - x0)) * w * (1.0 + 0.5 * sw);
+  if (sw > 0.0) return exp(s * (b - x0)) * expm1(-sw) / (-s);
+  return exp(s * (a - x0)) * expm1(sw) / s;
 }
 // inverse of the above: x in [a,b] with partial mass fraction q in (0,1).
 BNMF_HD double seg_inv(double s, double a, double b, double q) {
   double w = b - a;
   double sw = s * w;
   if (fabs(sw) < 1e-8) return a + q * w;
+  if (sw > 0.0) return b + log1p((1.0 - q) * expm1(-sw)) / s;
   return a + log1p(q * expm1(sw)) / s;
 }
 

@@ -128,9 +128,16 @@ int bnmf_get_map(bnmf_handle* h, int32_t n_samples, double* P_map, double* E_map
 int bnmf_comm_unique_id(char* id128);
 int bnmf_comm_init(bnmf_handle* h, const char* id128, int32_t rank, int32_t world);
 
-/* Device timing of the last bnmf_step call (CUDA events): total and the share of
- * the latent-count kernel, both in milliseconds; launches = kernels launched. */
-int bnmf_timing(bnmf_handle* h, double* total_ms, double* zstat_ms, int64_t* launches);
+/* Device timing of the last bnmf_step call (CUDA events on the handle's stream), in
+ * milliseconds: total = the whole call; iter = sum over iterations of the span from
+ * the first to the last kernel of the iteration; zstat = share of the latent-count
+ * kernel; launches = kernels launched. */
+int bnmf_timing(bnmf_handle* h, double* total_ms, double* iter_ms, double* zstat_ms, int64_t* launches);
+
+/* Benchmark hygiene: when bytes > 0, bnmf_step overwrites a scratch buffer of that size
+ * before every iteration (outside the spans bnmf_timing reports as iter_ms) so that each
+ * iteration starts with a cold L2.  0 switches it off (the default). */
+int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes);
 
 /* Stand-alone entry for the fused latent-count + sufficient-statistic kernel on the
  * handle's current P, E, A at iteration `iter` (parity tests, roofline timing).

@@ -143,21 +143,28 @@ def trigamma(x):
 
 
 def _seg_mass(s, a, b, x0):
+    """integral of exp(s (x - x0)) over [a, b], anchored at the end with the larger
+    exponent so that expm1 only ever sees a non-positive argument (no overflow)."""
     w = b - a
     sw = s * w
-    base = np.exp(s * (a - x0))
     small = np.abs(sw) < 1e-8
+    pos = sw > 0.0
+    base = np.exp(s * (np.where(pos, b, a) - x0))
     with np.errstate(divide="ignore", invalid="ignore"):
-        big = base * np.expm1(sw) / np.where(small, 1.0, s)
-    return np.where(small, base * w * (1.0 + 0.5 * sw), big)
+        big = base * np.expm1(-np.abs(sw)) / np.where(small, 1.0, np.where(pos, -s, s))
+    return np.where(small, np.exp(s * (a - x0)) * w * (1.0 + 0.5 * sw), big)
 
 
 def _seg_inv(s, a, b, q):
+    """x in [a, b] at partial mass fraction q of the segment above (same anchoring)."""
     w = b - a
     sw = s * w
     small = np.abs(sw) < 1e-8
+    pos = sw > 0.0
+    em = np.expm1(-np.abs(sw))
     with np.errstate(divide="ignore", invalid="ignore"):
-        big = a + np.log1p(q * np.expm1(sw)) / np.where(small, 1.0, s)
+        sd = np.where(small, 1.0, s)
+        big = np.where(pos, b + np.log1p((1.0 - q) * em) / sd, a + np.log1p(q * em) / sd)
     return np.where(small, a + q * w, big)
 
 

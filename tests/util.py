@@ -28,3 +28,10 @@ def synth_counts(K, G, N, mu_T=4000.0, seed=0):
     E = rng.gamma(1.0, mu_T / N, size=(N, G))
     M = rng.poisson(P @ E).astype(np.float64)
     return M, P, E
+
+
+def example_data():
+    """inst/extdata/example_data.rds of the reference (tests/golden/make_golden.py):
+    M 96 x 64 counts and the planted P 96 x 4 (COSMIC SBS58, SBS40, SBS26, SBS2)."""
+    d = np.load(os.path.join(GOLDEN, "example_data.npz"))
+    return d["M"].astype(np.float64), d["P"].astype(np.float64)
