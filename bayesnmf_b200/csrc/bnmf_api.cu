@@ -109,6 +109,19 @@ static __global__ void k_data_consts(const int32_t* Mi, long long n, double* out
   if (threadIdx.x == 0) { out[2 * blockIdx.x] = a; out[2 * blockIdx.x + 1] = b; }
 }
 
+// padded-KL constant of real-valued data: sum M' log M', M' = max(M, 1e-6)   (R/utils.R:467-471)
+template <typename T> static __global__ void k_data_consts_real(const T* Mr, long long n, double* out) {
+  __shared__ double sc[8];
+  double kl = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double m = (double)Mr[i];
+    const double mp = m > 1e-6 ? m : 1e-6;
+    kl += mp * log(mp);
+  }
+  const double b = block_sum<256>(kl, sc);
+  if (threadIdx.x == 0) { out[2 * blockIdx.x] = 0.0; out[2 * blockIdx.x + 1] = b; }
+}
+
 enum StType { ST_T, ST_I32, ST_U64 };
 struct StEntry { void* p; long long len; StType ty; };
 
@@ -229,8 +242,8 @@ struct Sampler : bnmf_handle {
     n_ktiles = (K + KT - 1) / KT;
     const int cts = (int)((G + 31) / 32);
     d.n_zitems = cts * n_ktiles * ((KT + 31) / 32);
-    d.n_eblocks = blocks(NG, 256);
-    if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
+    d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, 256);
+    if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + 2 * N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
         dalloc(&d.red, PC_COLS) || dalloc(&work_ctr, n_ktiles + 8) || dalloc(&nanflags, 5 * N)) return 1;
     if (dalloc(&d.ctrl, 1)) return 1;
     d.metrics_cap = 256;
@@ -270,6 +283,15 @@ struct Sampler : bnmf_handle {
       k_cvt_in<T><<<blocks(KG, 256), 256, 0, stream>>>(stage, mr, KG);
       d.Mr = mr;
       st["data"] = StEntry{mr, KG, ST_T};
+      const int nb = 296;
+      double* cpart; if (dalloc(&cpart, 2 * nb)) return 1;
+      k_data_consts_real<T><<<nb, 256, 0, stream>>>(mr, KG, cpart);
+      std::vector<double> hc(2 * nb);
+      CK(cudaMemcpyAsync(hc.data(), cpart, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      double b = 0;
+      for (int i = 0; i < nb; ++i) b += hc[2 * i + 1];
+      d.ll_const = 0.0; d.kl_const = b;
     }
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (z_config()) return 1; }
     if (mh_setup()) return 1;
@@ -321,6 +343,11 @@ struct Sampler : bnmf_handle {
   // ---- state I/O -------------------------------------------------------------------
   int set_hyper(const char* name, const double* v, int64_t rows, int64_t cols) override {
     CK(cudaSetDevice(cfg.device));
+    if (!strcmp(name, "alpha") || !strcmp(name, "beta")) {   // sigmasq prior scalars (R/bayesNMF_sampler.R:222-230)
+      if (rows * cols != 1) return fail("bnmf_set_hyper: '%s' is a scalar", name);
+      (name[0] == 'a' ? sig_alpha : sig_beta) = v[0];
+      return 0;
+    }
     auto it = hy.find(name);
     if (it == hy.end()) return fail("bnmf_set_hyper: unknown hyperparameter '%s'", name);
     long long n = (long long)rows * cols;
@@ -391,6 +418,8 @@ struct Sampler : bnmf_handle {
   // ---- cross-shard sum -----------------------------------------------------------
   int comm_init(const char* id, int rank_, int world_) override {
     CK(cudaSetDevice(cfg.device));
+    if (sweep_model)
+      return fail("bnmf_comm_init: genome sharding is built for the Poisson latent-count models; run Normal / MH models as independent chains, one per GPU");
     if (load_nccl()) return 1;
     Id128 uid; memcpy(uid.b, id, 128);
     int r = g_nccl.CommInitRank(&comm, world_, uid, rank_);
@@ -439,7 +468,11 @@ struct Sampler : bnmf_handle {
     return 0;
   }
   int rank_sweep();
+  int rank_sweep_kernels(int* pending);
   int refresh_metrics_only();
+  bool sweep_model = false; int h_converged = 0;
+  int p_kx = 32, p_gy = 8, p_ktiles = 1, col_blocks = 1, e_wpb = 8; size_t e_smem = 0;
+  double* asum = nullptr; double sig_alpha = 3.0, sig_beta = 3.0;
 
   int finish_iteration() {
     k_reduce_partials<T, 256><<<1, 256, 0, stream>>>(d); ++launches;
@@ -497,6 +530,7 @@ struct Sampler : bnmf_handle {
   int step(int n_iters, int converged, double* metrics, double* P_out, double* A_out) override {
     CK(cudaSetDevice(cfg.device));
     if (n_iters < 0) return fail("bnmf_step: n_iters < 0");
+    h_converged = converged ? 1 : 0;
     const int K = cfg.K, N = cfg.N; const long long KN = (long long)K * N;
     launches = 0;
     last_z_ms = 0; last_iter_ms = 0;

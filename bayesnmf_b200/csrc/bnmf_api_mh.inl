@@ -1,6 +1,127 @@
-// placeholder
-template <typename T> int Sampler<T>::mh_setup() { return 0; }
-template <typename T> int Sampler<T>::mh_iteration(int, uint32_t) { return fail("MH / Normal models: not built yet"); }
-template <typename T> int Sampler<T>::rank_sweep() { return fail("rank learning: not built yet"); }
-template <typename T> int Sampler<T>::refresh_metrics_only() { return fail("init with supplied Z: not built yet"); }
-template <typename T> int Sampler<T>::init_sigmasq_prior() { return 0; }
+// Host orchestration of the sweep-based models (Normal likelihood, Poisson + MH) and of
+// rank learning; kernels in bnmf_mh.cuh.  Included by bnmf_api.cu.
+
+template <typename T> static __global__ void k_ring_copy(Dev<T> d) {
+  // record_sample for P and E (R/bayesNMF_sampler.R:651-672); ring_A is written by k_metrics
+  const long long KN = (long long)d.K * d.N, NG = (long long)d.N * d.G;
+  const long long pos = d.ctrl->ring_pos;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < KN + NG; i += (long long)gridDim.x * blockDim.x) {
+    if (i < KN) d.ring_P[pos * KN + i] = d.P[i];
+    else d.ring_E[pos * NG + (i - KN)] = d.E[i - KN];
+  }
+}
+template <typename T> static __global__ void k_a_reduce(Dev<T> d, int nblocks, double* out) {
+  __shared__ double scratch[8];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { a += d.apart[2 * (long long)i]; b += d.apart[2 * (long long)i + 1]; }
+  const double l0 = block_sum<256>(a, scratch);
+  const double l1 = block_sum<256>(b, scratch);
+  if (threadIdx.x == 0) { out[0] = l0; out[1] = l1; }
+}
+template <typename T> int Sampler<T>::mh_setup() {
+  const int K = cfg.K, N = cfg.N; const long long G = cfg.G;
+  if (dalloc(&d.dvec, K) || dalloc(&d.prop, K) || dalloc(&d.nzE, 2 * N) || dalloc(&d.nzP, N) || dalloc(&d.paccpart, N) ||
+      dalloc(&asum, 2)) return 1;
+  sweep_model = cfg.MH || cfg.likelihood == BNMF_NORMAL;
+  if (!(sweep_model || cfg.learning_rank)) return 0;
+  // P sweep decomposition: KX mutation types x GY genome lanes per block, genomes in chunks
+  p_kx = ((K + 31) / 32) * 32; if (p_kx > 128) p_kx = 128;
+  p_gy = 256 / p_kx; if (p_gy < 1) p_gy = 1;
+  p_ktiles = (K + p_kx - 1) / p_kx;
+  long long chunks = (G + (long long)p_gy * 8 - 1) / ((long long)p_gy * 8);
+  const long long cap = std::max(1, 592 / p_ktiles);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  d.gchunk = (int)((G + chunks - 1) / chunks);
+  d.n_gchunks = (int)((G + d.gchunk - 1) / d.gchunk);
+  col_blocks = (int)((G + 7) / 8);
+  if (dalloc(&d.ppart, (long long)d.n_gchunks * K * 2) || dalloc(&d.apart, 2LL * col_blocks)) return 1;
+  // E sweep: warps per block limited by the shared-memory columns
+  const size_t budget = 220 * 1024;
+  long long w = ((long long)(budget / sizeof(double)) - K) / (2LL * K);
+  if (w < 1) return fail("k_e_sweep: K = %d does not fit one genome column in shared memory", K);
+  e_wpb = (int)std::min<long long>(8, w);
+  e_smem = (size_t)(1 + 2 * e_wpb) * K * sizeof(double);
+  CK(cudaFuncSetAttribute(k_e_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
+  return 0;
+}
+
+template <typename T> int Sampler<T>::rank_sweep_kernels(int* pending) {
+  const int N = cfg.N;
+  k_r<T><<<1, 32, 0, stream>>>(d); ++launches;
+  for (int n = 0; n < N; ++n) {
+    k_a_pass<T><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1); ++launches;
+    k_a_reduce<T><<<1, 256, 0, stream>>>(d, col_blocks, asum); ++launches;
+    if (allreduce_buf(asum, 2, NCCL_FLOAT64, NCCL_SUM)) return 1;
+    k_a_draw<T, 256><<<1, 256, 0, stream>>>(d, n, asum); ++launches;
+  }
+  *pending = N - 1;
+  return 0;
+}
+
+// rank learning inside the Poisson / latent-count iteration (R/sample_params.R:67-74)
+template <typename T> int Sampler<T>::rank_sweep() {
+  const long long KG = (long long)cfg.K * cfg.G;
+  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); ++launches;
+  int pending = -1;
+  return rank_sweep_kernels(&pending);   // the pending update is dropped: Mhat is rebuilt next iteration
+}
+
+template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have) {
+  const int K = cfg.K, N = cfg.N; const long long G = cfg.G;
+  const long long KN = (long long)K * N, NG = (long long)N * G, KG = (long long)K * G;
+  if (from_prior) {
+    if (!(have & BNMF_HAVE_P)) { k_prior_fill<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0); ++launches; }
+    if (!(have & BNMF_HAVE_E)) { k_prior_fill<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1); ++launches; }
+    k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); ++launches;
+    CK(cudaMemsetAsync(d.nzP, 0, sizeof(int) * N, stream));
+    CK(cudaMemsetAsync(d.nzE, 0, sizeof(int) * 2 * N, stream));
+    k_nzflags<T><<<blocks(std::max(KN, NG), 256), 256, 0, stream>>>(d); ++launches;
+    if (cfg.MH) {   // matrix(nrow, ncol) is NA-filled (R/bayesNMF_sampler.R:236-237)
+      k_fill<T><<<blocks(KN, 256), 256, 0, stream>>>(d.P_acc, KN, (T)NAN);
+      k_fill<T><<<blocks(NG, 256), 256, 0, stream>>>(d.E_acc, NG, (T)NAN);
+      launches += 2;
+    }
+    k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); ++launches;
+    k_final<T><<<col_blocks, 256, 0, stream>>>(d, -1, (have & BNMF_HAVE_SIGMASQ) ? 1 : 0); ++launches;
+  } else {
+    k_hyper<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0);
+    k_hyper<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1);
+    k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d);
+    launches += 3;
+    const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
+    const size_t psm = (size_t)p_kx * p_gy * 2 * sizeof(double);
+    const int dblocks = (K + 127) / 128;
+    for (int n = 0; n < N; ++n) {
+      k_p_pass1<T><<<pgrid, pblock, psm, stream>>>(d, n, n ? n - 1 : -1);
+      k_p_draw<T><<<dblocks, 128, 0, stream>>>(d, n);
+      launches += 2;
+      if (cfg.MH && h_converged) {
+        k_p_pass2<T><<<pgrid, pblock, psm, stream>>>(d, n);
+        k_p_accept<T><<<dblocks, 128, 0, stream>>>(d, n);
+        launches += 2;
+      }
+    }
+    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, N - 1); ++launches;
+    int pending = -1;
+    if (cfg.learning_rank) { if (rank_sweep_kernels(&pending)) return 1; }
+    k_final<T><<<col_blocks, 256, 0, stream>>>(d, pending, 0); ++launches;
+  }
+  k_pprior<T, 128><<<N, 128, 0, stream>>>(d); ++launches;
+  if (d.ring_cap > 0) { k_ring_copy<T><<<std::min(1024, blocks(KN + NG, 256)), 256, 0, stream>>>(d); ++launches; }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T> int Sampler<T>::refresh_metrics_only() {
+  return fail("bnmf_init_from_prior: a user-supplied Z cannot be honoured (the latent counts are never materialised; supply SP and SE instead)");
+}
+
+// Alpha_g = alpha, Beta_g = beta for every genome (R/sample_priors.R:133-140, the `%in%`
+// there tests values, so the vectors are always rebuilt from the scalars; defaults 3, 3:
+// R/bayesNMF_sampler.R:222-230)
+template <typename T> int Sampler<T>::init_sigmasq_prior() {
+  k_fill<T><<<blocks(cfg.G, 256), 256, 0, stream>>>(d.Alpha_g, cfg.G, (T)sig_alpha);
+  k_fill<T><<<blocks(cfg.G, 256), 256, 0, stream>>>(d.Beta_g, cfg.G, (T)sig_beta);
+  return 0;
+}

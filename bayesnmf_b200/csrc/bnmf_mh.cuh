@@ -1,4 +1,580 @@
-// placeholder, filled in below
+// Kernels of the sweep-based Gibbs iteration: the Normal likelihood, the Poisson
+// likelihood with Metropolis-Hastings proposals, and rank learning (SBFI / BFI).
+//
+//   prior parameters   R/sample_priors.R:214-308          k_hyper
+//   P sweep            R/sample_Pn.R:54-87,132-248        k_p_pass1 -> k_p_draw [-> k_p_pass2 -> k_p_accept]   per signature
+//   E sweep            R/sample_En.R:54-86,131-241        k_e_sweep                                            one launch
+//   R, A sweep         R/sample_params.R:101-241          k_r -> (k_a_pass -> k_a_draw)                        per signature
+//   sigmasq + metrics  R/sample_params.R:275-286, R/utils.R:412-455     k_final, k_pprior
+//
+// All of them work on a running reconstruction Mhat = P diag(A) E (K x G, resident in
+// HBM) that is corrected by rank-1 updates instead of being recomputed by a dgemm per
+// conditional as the reference does (2 to 8 get_Mhat calls per signature,
+// R/sample_Pn.R:136,152,209-231).  A changed column of P (or a flipped A_n) is applied
+// lazily: the next pass that streams Mhat anyway adds dvec[k] * E[n_prev, g] on the fly.
+// The sweeps over n are truly sequential (each conditional sees the columns already
+// updated), which is why P needs one streaming pass per signature while E -- whose
+// conditionals are independent across genomes -- runs all N updates of a column
+// on-chip in one launch.
 #pragma once
+#include "bnmf_poisson.cuh"
 #include "bnmf_rng.cuh"
 #include "bnmf_state.h"
+
+namespace bnmf {
+
+constexpr double LOG_SQRT_2PI = 0.9189385332046727;
+
+// log(pnorm(t)), stable in both tails
+__device__ __forceinline__ double log_ndtr(double t) {
+  if (t >= 0.0) return log1p(-0.5 * erfc(t * 0.7071067811865476));
+  return log(0.5 * erfcx(-t * 0.7071067811865476)) - 0.5 * t * t;
+}
+// log(truncnorm::dtruncnorm(x, a = 0, b = Inf, mean, sd))   (R/utils.R:134-145)
+__device__ __forceinline__ double dtruncnorm0_log(double x, double mean, double sd) {
+  const double z = (x - mean) / sd;
+  return -LOG_SQRT_2PI - log(sd) - 0.5 * z * z - log_ndtr(mean / sd);
+}
+__device__ __forceinline__ double dnorm_log(double x, double mean, double var) {
+  const double r = x - mean;
+  return -LOG_SQRT_2PI - 0.5 * log(var) - 0.5 * (r * r) / var;
+}
+template <typename T> __device__ __forceinline__ double Mat(const Dev<T>& d, long long i) {
+  return d.likelihood == LIK_POISSON ? (double)d.Mi[i] : (double)d.Mr[i];
+}
+// log Metropolis-Hastings ratio contribution of one cell (R/sample_Pn.R:213-238):
+// dpois(M; new) - dpois(M; old) + dnorm(M; old, var = max(new, 1)) - dnorm(M; new, var = max(old, 1));
+// the lgamma(M + 1) and -log sqrt(2 pi) terms cancel inside the cell.
+__device__ __forceinline__ double mh_cell(double m, double mh_old, double mh_new) {
+  const double lo = mh_old > 1e-6 ? mh_old : 1e-6, ln = mh_new > 1e-6 ? mh_new : 1e-6;
+  const double dp = (m * log(ln) - ln) - (m * log(lo) - lo);
+  const double vo = mh_new > 1.0 ? mh_new : 1.0, vn = mh_old > 1.0 ? mh_old : 1.0;
+  const double ro = m - mh_old, rn = m - mh_new;
+  const double n_old = -0.5 * log(vo) - 0.5 * (ro * ro) / vo;
+  const double n_new = -0.5 * log(vn) - 0.5 * (rn * rn) / vn;
+  return dp + (n_old - n_new);
+}
+__device__ __forceinline__ double mh_ratio(double D) {
+  if (!(D == D)) return D;           // NaN stays NaN: the comparison u < NaN rejects
+  const double r = exp(D);
+  return r < 1.0 ? r : 1.0;
+}
+
+// draw of one element from its prior (R/sample_Pn.R:12-30,56-74; R/sample_En.R:12-30,56-73)
+template <typename T>
+__device__ __forceinline__ double prior_draw(const Dev<T>& d, const Stream& st, int side, long long idx) {
+  if (d.prior == PRIOR_TRUNCNORMAL) {
+    const double mu = (double)(side == 0 ? d.Mu_p : d.Mu_e)[idx];
+    const double sg = (double)(side == 0 ? d.Sigmasq_p : d.Sigmasq_e)[idx];
+    return truncnorm0_draw<double>(st, mu, sqrt(sg));
+  }
+  if (d.prior == PRIOR_EXPONENTIAL)
+    return gamma_draw<double>(st, 1.0, (double)(side == 0 ? d.Lambda_p : d.Lambda_e)[idx]);
+  return gamma_draw<double>(st, (double)(side == 0 ? d.Alpha_p : d.Alpha_e)[idx],
+                            (double)(side == 0 ? d.Beta_p : d.Beta_e)[idx]);
+}
+template <typename T>
+__device__ __forceinline__ double prior_logdens(const Dev<T>& d, int side, long long idx, double x) {
+  if (d.prior == PRIOR_TRUNCNORMAL)
+    return dtruncnorm0_log(x, (double)(side == 0 ? d.Mu_p : d.Mu_e)[idx],
+                           sqrt((double)(side == 0 ? d.Sigmasq_p : d.Sigmasq_e)[idx]));
+  if (d.prior == PRIOR_EXPONENTIAL) return dexp_log(x, (double)(side == 0 ? d.Lambda_p : d.Lambda_e)[idx]);
+  return dgamma_log(x, (double)(side == 0 ? d.Alpha_p : d.Alpha_e)[idx], (double)(side == 0 ? d.Beta_p : d.Beta_e)[idx]);
+}
+
+// ------------------------------------------------------------------------------
+// k_hyper: prior-parameter updates of the truncated-normal and exponential priors,
+// element-wise (they read only the previous P / E; R/sample_priors.R:214-308).
+//   Mu ~ N(num/den, sd = 1/den)      -- the reference passes the variance as sd (:219,:235)
+//   Sigmasq ~ InvGamma(A + 1/2, B + (X - Mu)^2 / 2), the E side with A_e as base (:267)
+//   Lambda ~ Gamma(A + 1, B + X)
+// ------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_hyper(Dev<T> d, int side) {
+  const int K = d.K, N = d.N;
+  const long long cells = side == 0 ? (long long)K * N : (long long)N * d.G;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells) return;
+  const long long c = side == 0 ? idx : (idx % N) + (long long)N * (d.g0 + idx / N);
+  const int iter = d.ctrl->iter;
+  const uint32_t pur1 = side == 0 ? PUR_HYP_P1 : PUR_HYP_E1, pur2 = side == 0 ? PUR_HYP_P2 : PUR_HYP_E2;
+  const Hyper<T>& hA = side == 0 ? d.A_p : d.A_e;
+  const Hyper<T>& hB = side == 0 ? d.B_p : d.B_e;
+  const double X = (double)(side == 0 ? d.P : d.E)[idx];
+  if (d.prior == PRIOR_TRUNCNORMAL) {
+    const Hyper<T>& hM = side == 0 ? d.M_p : d.M_e;
+    const Hyper<T>& hS = side == 0 ? d.S_p : d.S_e;
+    T* Mu = side == 0 ? d.Mu_p : d.Mu_e;
+    T* Sg = side == 0 ? d.Sigmasq_p : d.Sigmasq_e;
+    const double S = (double)hS.at(idx), sg = (double)Sg[idx];
+    const double num = (double)hM.at(idx) / S + X / sg;
+    const double den = 1.0 / S + 1.0 / sg;
+    const double mu = (double)(T)normal_draw<double>(make_stream(d.seed, iter, pur1, c), num / den, 1.0 / den);
+    Mu[idx] = (T)mu;
+    const double base = side == 0 ? (double)hB.at(idx) : (double)hA.at(idx);
+    const double r = X - mu;
+    Sg[idx] = (T)(1.0 / gamma_draw<double>(make_stream(d.seed, iter, pur2, c), (double)hA.at(idx) + 0.5, base + (r * r) / 2.0));
+  } else if (d.prior == PRIOR_EXPONENTIAL) {
+    T* La = side == 0 ? d.Lambda_p : d.Lambda_e;
+    La[idx] = (T)gamma_draw<double>(make_stream(d.seed, iter, pur1, c), (double)hA.at(idx) + 1.0, (double)hB.at(idx) + X);
+  }
+}
+
+// k_prior_fill: P or E entirely from the prior (iteration 1, R/bayesNMF_sampler.R:241).
+template <typename T>
+__global__ void k_prior_fill(Dev<T> d, int side) {
+  const int K = d.K, N = d.N;
+  const long long cells = side == 0 ? (long long)K * N : (long long)N * d.G;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells) return;
+  const long long c = side == 0 ? idx : (idx % N) + (long long)N * (d.g0 + idx / N);
+  const Stream st = make_stream(d.seed, d.ctrl->iter, side == 0 ? PUR_P : PUR_E, c);
+  (side == 0 ? d.P : d.E)[idx] = (T)prior_draw(d, st, side, idx);
+}
+
+// non-zero flags of the columns of P / rows of E, and NaN acceptance rates (iteration 1)
+template <typename T>
+__global__ void k_nzflags(Dev<T> d) {
+  const int K = d.K, N = d.N;
+  const int iter = d.ctrl->iter;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)K * N && d.P[i] != (T)0) atomicOr(&d.nzP[i / K], 1);
+  if (i < (long long)N * d.G && d.E[i] != (T)0) atomicOr(&d.nzE[(iter & 1) * N + (int)(i % N)], 1);
+}
+template <typename T> __global__ void k_fill(T* p, long long n, T v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// k_mhat_full: Mhat = P diag(A) E from scratch (get_Mhat_, R/utils.R:29-49); run once per
+// iteration so that rounding of the rank-1 corrections cannot accumulate.
+template <typename T>
+__global__ void k_mhat_full(Dev<T> d) {
+  const int K = d.K, N = d.N;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)K * d.G) return;
+  const int k = (int)(i % K);
+  const long long g = i / K;
+  double acc = 0.0;
+  for (int n = 0; n < N; ++n)
+    if (d.A[n]) acc += (double)d.P[k + (long long)K * n] * (double)d.E[n + (long long)N * g];
+  d.Mhat[i] = (T)acc;
+}
+
+// ------------------------------------------------------------------------------
+// P sweep, signature n.  Thread (kx, gy) owns mutation type k and every GY-th genome of
+// the block's chunk; a warp reads 32 consecutive k of one genome (coalesced, K is the
+// fast axis of M and Mhat).  The reduction over genomes is a private running sum per
+// thread, combined over gy in shared memory and over chunks by k_p_draw, both in a
+// fixed order (bit-reproducible).
+//   pass 1: apply the pending rank-1 update, then
+//           num1[k] = sum_g E[n,g] (M - Mhat_{-n})[k,g] / s[k,g],  den[k] = sum_g A_n E[n,g]^2 / s[k,g]
+//           with s = Mhat (MH proposal, R/sample_Pn.R:137-139) or s = sigmasq_g (Normal)
+//   pass 2: log MH ratio of the proposal (R/sample_Pn.R:206-238), only after convergence
+// ------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_p_pass1(Dev<T> d, int n, int n_prev) {
+  extern __shared__ double sm[];
+  const int K = d.K, N = d.N;
+  const int kx = threadIdx.x, gy = threadIdx.y, GY = blockDim.y, KX = blockDim.x;
+  const int k = blockIdx.y * KX + kx;
+  const long long gbeg = (long long)blockIdx.x * d.gchunk;
+  const long long gend = gbeg + d.gchunk < d.G ? gbeg + d.gchunk : d.G;
+  const int An = d.A[n];
+  const bool normal = d.likelihood == LIK_NORMAL;
+  double num1 = 0.0, den = 0.0;
+  if (k < K) {
+    const double dv = n_prev >= 0 ? d.dvec[k] : 0.0;
+    const double pkn = (double)d.P[k + (long long)K * n];
+    for (long long g = gbeg + gy; g < gend; g += GY) {
+      const long long i = k + (long long)K * g;
+      double mh = (double)d.Mhat[i];
+      if (n_prev >= 0) {
+        mh = (double)(T)(mh + dv * (double)d.E[n_prev + (long long)N * g]);
+        d.Mhat[i] = (T)mh;
+      }
+      if (An) {
+        const double e = (double)d.E[n + (long long)N * g];
+        const double s = normal ? (double)d.sigmasq[g] : mh;
+        const double mh_no = mh - pkn * e;
+        num1 += e * ((Mat(d, i) - mh_no) / s);
+        den += (e * e) * (1.0 / s);
+      }
+    }
+  }
+  sm[(gy * KX + kx) * 2 + 0] = num1;
+  sm[(gy * KX + kx) * 2 + 1] = den;
+  __syncthreads();
+  if (gy == 0 && k < K) {
+    for (int y = 1; y < GY; ++y) { num1 += sm[(y * KX + kx) * 2 + 0]; den += sm[(y * KX + kx) * 2 + 1]; }
+    double* pp = d.ppart + ((long long)blockIdx.x * K + k) * 2;
+    pp[0] = num1; pp[1] = den;
+  }
+}
+
+template <typename T>
+__global__ void k_p_pass2(Dev<T> d, int n) {
+  extern __shared__ double sm[];
+  const int K = d.K, N = d.N;
+  const int kx = threadIdx.x, gy = threadIdx.y, GY = blockDim.y, KX = blockDim.x;
+  const int k = blockIdx.y * KX + kx;
+  const long long gbeg = (long long)blockIdx.x * d.gchunk;
+  const long long gend = gbeg + d.gchunk < d.G ? gbeg + d.gchunk : d.G;
+  double D = 0.0;
+  if (k < K && d.A[n]) {
+    const double dp = d.prop[k] - (double)d.P[k + (long long)K * n];
+    for (long long g = gbeg + gy; g < gend; g += GY) {
+      const long long i = k + (long long)K * g;
+      const double mh = (double)d.Mhat[i];
+      D += mh_cell(Mat(d, i), mh, mh + dp * (double)d.E[n + (long long)N * g]);
+    }
+  }
+  sm[gy * KX + kx] = D;
+  __syncthreads();
+  if (gy == 0 && k < K) {
+    for (int y = 1; y < GY; ++y) D += sm[y * KX + kx];
+    d.ppart[((long long)blockIdx.x * K + k) * 2] = D;
+  }
+}
+
+// k_p_draw: finish the reduction, form the conditional (or proposal) moments, draw.
+template <typename T>
+__global__ void k_p_draw(Dev<T> d, int n) {
+  const int K = d.K, N = d.N;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int iter = d.ctrl->iter;
+  const int An = d.A[n];
+  const long long c = k + (long long)K * n;
+  const double Pold = (double)d.P[c];
+  const Stream st = make_stream(d.seed, iter, PUR_P, c);
+  const bool zero_row = d.nzE[((iter - 1) & 1) * N + n] == 0;   // all(E[n, ] == 0), R/sample_Pn.R:56
+  double x;
+  if (An == 0 || zero_row) {
+    x = prior_draw(d, st, 0, c);
+  } else {
+    double num1 = 0.0, den = 0.0;
+    for (int ch = 0; ch < d.n_gchunks; ++ch) {
+      const double* pp = d.ppart + ((long long)ch * K + k) * 2;
+      num1 += pp[0]; den += pp[1];
+    }
+    double mu, v;
+    if (d.prior == PRIOR_EXPONENTIAL) {
+      mu = (num1 - (double)d.Lambda_p[c]) / den; v = 1.0 / den;
+    } else {
+      const double sg = (double)d.Sigmasq_p[c];
+      den = den + 1.0 / sg;
+      mu = (num1 + (double)d.Mu_p[c] / sg) / den; v = 1.0 / den;
+    }
+    x = truncnorm0_draw<double>(st, mu, sqrt(v));
+  }
+  x = (double)(T)x;
+  const bool mh_step = d.MH && d.ctrl->converged && An != 0;
+  if (mh_step) {                      // k_p_pass2 / k_p_accept decide
+    d.prop[k] = x;
+    d.dvec[k] = 0.0;
+    return;
+  }
+  if (d.MH && An != 0) d.P_acc[c] = (T)1;                        // R/sample_Pn.R:201-204
+  d.P[c] = (T)x;
+  d.dvec[k] = An ? x - Pold : 0.0;
+  if (x != 0.0) atomicOr(&d.nzP[n], 1);
+}
+
+template <typename T>
+__global__ void k_p_accept(Dev<T> d, int n) {
+  const int K = d.K;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K || d.A[n] == 0) return;
+  const long long c = k + (long long)K * n;
+  double D = 0.0;
+  for (int ch = 0; ch < d.n_gchunks; ++ch) D += d.ppart[((long long)ch * K + k) * 2];
+  const double ratio = mh_ratio(D);
+  d.P_acc[c] = (T)ratio;
+  const double u = u01<double>(make_stream(d.seed, d.ctrl->iter, PUR_MH_P, c).at(0).x);
+  const double Pold = (double)d.P[c];
+  const double x = u < ratio ? d.prop[k] : Pold;
+  d.P[c] = (T)x;
+  d.dvec[k] = x - Pold;
+  if (x != 0.0) atomicOr(&d.nzP[n], 1);
+}
+
+// ------------------------------------------------------------------------------
+// k_e_sweep: all N updates of E[., g] for one genome per warp.  The genome's column of M
+// and of the running Mhat stay in shared memory for the whole sweep; column n of P is
+// staged once per block and shared by its warps; the reductions over k are warp
+// butterflies (fixed order).  One streaming pass over M and Mhat per iteration, whatever N.
+// ------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_e_sweep(Dev<T> d, int n_prev) {
+  extern __shared__ double sm[];
+  const int K = d.K, N = d.N;
+  const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Pn = sm;
+  double* Mh = sm + K + (size_t)wid * 2 * K;
+  double* Mv = Mh + K;
+  const long long g = (long long)blockIdx.x * WPB + wid;
+  const bool valid = g < d.G;
+  const int iter = d.ctrl->iter, converged = d.ctrl->converged;
+  const bool normal = d.likelihood == LIK_NORMAL;
+  if (valid) {
+    const double eprev = n_prev >= 0 ? (double)d.E[n_prev + (long long)N * g] : 0.0;
+    for (int k = lane; k < K; k += 32) {
+      const long long i = k + (long long)K * g;
+      double mh = (double)d.Mhat[i];
+      if (n_prev >= 0) mh = (double)(T)(mh + d.dvec[k] * eprev);
+      Mh[k] = mh;
+      Mv[k] = Mat(d, i);
+    }
+  }
+  const double sg = (valid && normal) ? (double)d.sigmasq[g] : 0.0;
+  for (int n = 0; n < N; ++n) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) Pn[k] = (double)d.P[k + (long long)K * n];
+    __syncthreads();
+    if (!valid) continue;
+    const int An = d.A[n];
+    const long long idx = n + (long long)N * g;
+    const long long c = n + (long long)N * (d.g0 + g);
+    const double Eold = (double)d.E[idx];
+    const Stream st = make_stream(d.seed, iter, PUR_E, c);
+    double x;
+    if (An == 0 || d.nzP[n] == 0) {                               // R/sample_En.R:12,56
+      x = prior_draw(d, st, 1, idx);
+    } else {
+      double num1 = 0.0, den = 0.0;
+      for (int k = lane; k < K; k += 32) {
+        const double mh = Mh[k], p = Pn[k];
+        const double s = normal ? sg : mh;
+        const double mh_no = mh - p * Eold;
+        num1 += p * ((Mv[k] - mh_no) / s);
+        den += (p * p) * (1.0 / s);
+      }
+      num1 = warp_sum(num1); den = warp_sum(den);
+      double mu, v;
+      if (d.prior == PRIOR_EXPONENTIAL) {
+        mu = (num1 - (double)d.Lambda_e[idx]) / den; v = 1.0 / den;
+      } else {
+        const double s2 = (double)d.Sigmasq_e[idx];
+        den = den + 1.0 / s2;
+        mu = (num1 + (double)d.Mu_e[idx] / s2) / den; v = 1.0 / den;
+      }
+      x = truncnorm0_draw<double>(st, mu, sqrt(v));
+    }
+    x = (double)(T)x;
+    double Enew = x;
+    if (d.MH && An != 0) {
+      if (!converged) {
+        if (lane == 0) d.E_acc[idx] = (T)1;                         // R/sample_En.R:198-201
+      } else {
+        double D = 0.0;
+        const double de = x - Eold;
+        for (int k = lane; k < K; k += 32) { const double mh = Mh[k]; D += mh_cell(Mv[k], mh, mh + Pn[k] * de); }
+        D = warp_sum(D);
+        const double ratio = mh_ratio(D);
+        if (lane == 0) d.E_acc[idx] = (T)ratio;
+        const double u = u01<double>(make_stream(d.seed, iter, PUR_MH_E, c).at(0).x);
+        Enew = u < ratio ? x : Eold;
+      }
+    }
+    if (An != 0 && Enew != Eold) {
+      const double de = Enew - Eold;
+      for (int k = lane; k < K; k += 32) Mh[k] = (double)(T)(Mh[k] + Pn[k] * de);
+    }
+    if (lane == 0) {
+      d.E[idx] = (T)Enew;
+      if (Enew != 0.0) atomicOr(&d.nzE[(iter & 1) * N + n], 1);
+    }
+    __syncwarp();
+  }
+  if (valid)
+    for (int k = lane; k < K; k += 32) d.Mhat[k + (long long)K * g] = (T)Mh[k];
+}
+
+// ------------------------------------------------------------------------------
+// Rank learning (R/sample_params.R:101-241).
+// k_r: R | A  ~ categorical over 0..N with weight (q_r^{sum A} (1 - q_r)^{N - sum A})^T.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ double prior_prob_1(double R, int N) {   // compute_prior_prob_1, :178-187
+  double q = R / (double)N;
+  const double c = 0.4 / (double)N;
+  if (q < c) q = c;
+  if (q > 1.0 - c) q = 1.0 - c;
+  return q;
+}
+template <typename T> __device__ __forceinline__ double temperature(const Dev<T>& d, int iter) {
+  return (iter >= 1 && iter <= d.n_temps) ? d.temps[iter - 1] : 1.0;
+}
+template <typename T>
+__global__ void k_r(Dev<T> d) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int N = d.N, iter = d.ctrl->iter;
+  const double Tm = temperature(d, iter);
+  int sA = 0;
+  for (int n = 0; n < N; ++n) sA += d.A[n];
+  double probs[65], tot = 0.0;
+  for (int r = 0; r <= N; ++r) {
+    const double q = prior_prob_1((double)r, N);
+    probs[r] = (1.0 / (double)(N + 1)) * pow(pow(q, (double)sA) * pow(1.0 - q, (double)(N - sA)), Tm);
+    tot += probs[r];
+  }
+  const double u = u01<double>(make_stream(d.seed, iter, PUR_R, 0).at(0).x);
+  double cdf = 0.0;
+  int r = 0;
+  for (int j = 0; j <= N; ++j) { cdf += probs[j] / tot; if (cdf <= u) ++r; }
+  *d.R = r < N ? r : N;
+}
+
+// k_a_pass: one streaming pass giving the log-likelihood with A_n = 0 and with A_n = 1
+// (the two get_loglik calls of R/sample_params.R:115-116); a warp per genome column.
+template <typename T>
+__global__ void k_a_pass(Dev<T> d, int n, int n_prev) {
+  __shared__ double s0[32], s1[32];
+  const int K = d.K, N = d.N;
+  const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long g = (long long)blockIdx.x * WPB + wid;
+  const bool normal = d.likelihood == LIK_NORMAL;
+  double l0 = 0.0, l1 = 0.0;
+  if (g < d.G) {
+    const int An = d.A[n];
+    const double e = (double)d.E[n + (long long)N * g];
+    const double eprev = n_prev >= 0 ? (double)d.E[n_prev + (long long)N * g] : 0.0;
+    const double sg = normal ? (double)d.sigmasq[g] : 0.0;
+    for (int k = lane; k < K; k += 32) {
+      const long long i = k + (long long)K * g;
+      double mh = (double)d.Mhat[i];
+      if (n_prev >= 0) { mh = (double)(T)(mh + d.dvec[k] * eprev); d.Mhat[i] = (T)mh; }
+      const double pe = (double)d.P[k + (long long)K * n] * e;
+      const double mh0 = An ? mh - pe : mh, mh1 = An ? mh : mh + pe;
+      const double m = Mat(d, i);
+      if (normal) { l0 += dnorm_log(m, mh0, sg); l1 += dnorm_log(m, mh1, sg); }
+      else {
+        const double a = mh0 > 1e-6 ? mh0 : 1e-6, b = mh1 > 1e-6 ? mh1 : 1e-6;
+        l0 += m * log(a) - a; l1 += m * log(b) - b;
+      }
+    }
+  }
+  l0 = warp_sum(l0); l1 = warp_sum(l1);
+  if (lane == 0) { s0[wid] = l0; s1[wid] = l1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < WPB; ++w) { a += s0[w]; b += s1[w]; }
+    d.apart[2 * (long long)blockIdx.x] = a; d.apart[2 * (long long)blockIdx.x + 1] = b;
+  }
+}
+
+// k_a_draw: A_n ~ Bernoulli(p), SBFI / BFI (R/sample_params.R:118-165); one block.
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_a_draw(Dev<T> d, int n, const double* lsum) {
+  __shared__ int s_delta;
+  const int K = d.K, N = d.N;
+  double l0 = lsum[0], l1 = lsum[1];
+  if (threadIdx.x == 0) {
+    const int iter = d.ctrl->iter;
+    if (d.likelihood == LIK_POISSON) { l0 += d.ll_const; l1 += d.ll_const; }
+    const double q = prior_prob_1((double)*d.R, N);
+    const double Tm = temperature(d, iter);
+    const int Aold = d.A[n];
+    int sA = 0;
+    for (int j = 0; j < N; ++j) sA += d.A[j];
+    const double sA0 = (double)(sA - Aold), sA1 = sA0 + 1.0;
+    double lp0, lp1;
+    if (d.rank_method == RANK_SBFI) {
+      const double GK = (double)d.G_total + (double)K, lg = log((double)d.G_total);
+      const double b0 = l0 - sA0 * GK * lg / 2.0, b1 = l1 - sA1 * GK * lg / 2.0;
+      lp0 = log(1.0 - q) + Tm * b0; lp1 = log(q) + Tm * b1;
+    } else {
+      lp0 = log(1.0 - q) + Tm * l0; lp1 = log(q) + Tm * l1;
+    }
+    const double hi = lp0 > lp1 ? lp0 : lp1, lo = lp0 > lp1 ? lp1 : lp0;
+    const double s = hi + log(1.0 + exp(lo - hi));                 // sumLog, :199-206
+    double p = exp(lp1 - s);
+    if (!(p == p)) {                                               // overflow branch, :143-163
+      const bool n1 = !(lp1 == lp1), n0 = !(lp0 == lp0);
+      if (n1 && n0) p = 0.5; else if (n1) p = 0.0; else if (n0) p = 1.0;
+      else if (lp1 > lp0) p = 1.0; else if (lp1 < lp0) p = 0.0; else p = 0.5;
+    }
+    const double u = u01<double>(make_stream(d.seed, iter, PUR_A, (uint64_t)n).at(0).x);
+    const int Anew = u < p ? 1 : 0;
+    d.A[n] = Anew;
+    s_delta = Anew - Aold;
+  }
+  __syncthreads();
+  const double dl = (double)s_delta;
+  for (int k = threadIdx.x; k < K; k += THREADS) d.dvec[k] = dl * (double)d.P[k + (long long)K * n];
+}
+
+// ------------------------------------------------------------------------------
+// k_final: last streaming pass of the iteration, a warp per genome column:
+//   apply the pending update; sigmasq_g ~ InvGamma(Alpha_g + K/2, Beta_g + SSE_g / 2)
+//   (R/sample_params.R:275-286); metric partials (log-likelihood, SSE, padded KL;
+//   R/utils.R:412-455, :467-471); log prior of E[., g] and the E acceptance sum.
+// ------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_final(Dev<T> d, int n_prev, int keep_sigmasq) {
+  __shared__ double sp[32][PC_COLS];
+  const int K = d.K, N = d.N;
+  const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long g = (long long)blockIdx.x * WPB + wid;
+  const bool normal = d.likelihood == LIK_NORMAL;
+  double sse = 0.0, ll = 0.0, kl = 0.0, lpe = 0.0, eacc = 0.0;
+  if (g < d.G) {
+    const double eprev = n_prev >= 0 ? (double)d.E[n_prev + (long long)N * g] : 0.0;
+    for (int k = lane; k < K; k += 32) {
+      const long long i = k + (long long)K * g;
+      double mh = (double)d.Mhat[i];
+      if (n_prev >= 0) { mh = (double)(T)(mh + d.dvec[k] * eprev); d.Mhat[i] = (T)mh; }
+      const double r = Mat(d, i) - mh;
+      sse += r * r;
+    }
+    sse = warp_sum(sse);
+    double sg = 0.0;
+    if (normal) {
+      if (!keep_sigmasq) {
+        sg = (double)(T)(1.0 / gamma_draw<double>(make_stream(d.seed, d.ctrl->iter, PUR_SIGMASQ, (uint64_t)(d.g0 + g)),
+                                                  (double)d.Alpha_g[g] + (double)K / 2.0, (double)d.Beta_g[g] + 0.5 * sse));
+        if (lane == 0) d.sigmasq[g] = (T)sg;
+      } else sg = (double)d.sigmasq[g];
+    }
+    for (int k = lane; k < K; k += 32) {
+      const long long i = k + (long long)K * g;
+      const double mh = (double)d.Mhat[i], m = Mat(d, i);
+      const double lam = mh > 1e-6 ? mh : 1e-6;
+      const double L = log(lam);
+      kl -= (m > 1e-6 ? m : 1e-6) * L;
+      ll += normal ? dnorm_log(m, mh, sg) : m * L - lam;
+    }
+    for (int n = lane; n < N; n += 32) {
+      const long long idx = n + (long long)N * g;
+      lpe += prior_logdens(d, 1, idx, (double)d.E[idx]);
+      if (d.MH && d.A[n]) eacc += (double)d.E_acc[idx];
+    }
+    ll = warp_sum(ll); kl = warp_sum(kl); lpe = warp_sum(lpe); eacc = warp_sum(eacc);
+  }
+  if (lane == 0) { sp[wid][PC_SSE] = sse; sp[wid][PC_KLV] = kl; sp[wid][PC_LLV] = ll; sp[wid][PC_LP_E] = lpe; sp[wid][PC_EACC] = eacc; }
+  __syncthreads();
+  if (threadIdx.x < PC_COLS) {
+    double s = 0.0;
+    for (int w = 0; w < WPB; ++w) s += sp[w][threadIdx.x];
+    d.epart[(long long)blockIdx.x * PC_COLS + threadIdx.x] = s;
+  }
+}
+
+// k_pprior: log prior of column n of P and the sum of its acceptance rates (block n).
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_pprior(Dev<T> d) {
+  __shared__ double scratch[THREADS / 32];
+  const int n = blockIdx.x, K = d.K;
+  double lp = 0.0, pa = 0.0;
+  for (int k = threadIdx.x; k < K; k += THREADS) {
+    const long long c = k + (long long)K * n;
+    lp += prior_logdens(d, 0, c, (double)d.P[c]);
+    if (d.MH) pa += (double)d.P_acc[c];
+  }
+  const double a = block_sum<THREADS>(lp, scratch);
+  const double b = block_sum<THREADS>(pa, scratch);
+  if (threadIdx.x == 0) { d.zpart[(long long)d.n_zitems * PC_COLS + n] = a; d.paccpart[n] = b; }
+}
+
+}  // namespace bnmf

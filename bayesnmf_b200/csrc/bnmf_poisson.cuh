@@ -47,9 +47,13 @@ __device__ __forceinline__ double dexp_log(double x, double rate) { return log(r
 template <typename T>
 __global__ void k_begin_iter(Dev<T> d, int* work_ctr, int n_ctr) {
   const int t = threadIdx.x;
-  if (t == 0) { d.ctrl->iter += 1; d.ctrl->row += 1; }
-  if (t < n_ctr) work_ctr[t] = 0;
+  const int iter = d.ctrl->iter + 1;
+  __syncthreads();
+  if (t == 0) { d.ctrl->iter = iter; d.ctrl->row += 1; }
+  for (int i = t; i < n_ctr; i += blockDim.x) work_ctr[i] = 0;
   if (t == 0) { *d.lp_P = 0.0; *d.pacc_sum = 0.0; }
+  // non-zero flags written during this iteration (bnmf_mh.cuh)
+  for (int n = t; n < d.N; n += blockDim.x) { d.nzP[n] = 0; d.nzE[(iter & 1) * d.N + n] = 0; }
 }
 
 // ------------------------------------------------------------------------------
@@ -424,8 +428,11 @@ __global__ void k_metrics(Dev<T> d) {
   m[MC_RANK] = (double)rank;
   m[MC_TEMP] = (c->iter >= 1 && c->iter <= d.n_temps) ? d.temps[c->iter - 1] : 1.0;
   if (d.MH) {
-    const double na = rank > 0 ? (double)rank : 1.0;
-    m[MC_PACC] = *d.pacc_sum / (na * (double)d.K);
+    // mean over the active signatures (R/utils.R:444-452); NaN when none is active
+    double pa = 0.0;
+    for (int n = 0; n < d.N; ++n) if (d.A[n]) pa += d.paccpart[n];
+    const double na = rank > 0 ? (double)rank : nan("");
+    m[MC_PACC] = pa / (na * (double)d.K);
     m[MC_EACC] = d.red[PC_EACC] / (na * (double)d.G_total);
   } else {
     m[MC_PACC] = 1.0; m[MC_EACC] = 1.0;

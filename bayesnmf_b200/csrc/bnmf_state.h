@@ -85,8 +85,17 @@ template <typename T> struct Dev {
 
   // acceptance rates (MH)
   T* P_acc; T* E_acc;
-  // running reconstruction (MH / Normal paths)
+  // running reconstruction Mhat = P diag(A) E (MH / Normal / rank-learning paths) and the
+  // scratch of the sequential sweeps over signatures (bnmf_mh.cuh)
   T* Mhat;
+  double* dvec;      // K: pending rank-1 update  Mhat[k,g] += dvec[k] * E[n_prev,g]
+  double* prop;      // K: proposal for column n of P awaiting the accept step
+  double* ppart;     // [n_gchunks][K][2] partial sums over genome chunks (P sweep)
+  int n_gchunks, gchunk;
+  double* apart;     // [n_eblocks][2] log-likelihood partials with A_n = 0 / 1
+  int* nzE;          // [2][N] "row n of E has a non-zero" flags, by iteration parity
+  int* nzP;          // [N]    "column n of P has a non-zero" flags
+  double* paccpart;  // [N] sum_k P_acceptance_rate[k,n]
 
   // per-tile deterministic partials
   double* zpart;   int n_zitems;     // [n_zitems][PC_COLS] written by the column kernels
