@@ -135,7 +135,8 @@ struct Sampler : bnmf_handle {
   std::map<std::string, Hyper<T>*> hy;
   std::map<std::string, long long> hy_len;
   double* stage = nullptr; long long stage_len = 0;      // device double staging
-  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96;
+  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96; int ZR = 32;
+  double* red_slices = nullptr; unsigned* red_ticket = nullptr;
   int* nanflags = nullptr;
   T* P_hist = nullptr; int32_t* A_hist = nullptr;
   double* h_metrics = nullptr;                            // pinned
@@ -233,19 +234,22 @@ struct Sampler : bnmf_handle {
     // work decomposition of the column kernels: the k-tile is the largest multiple of 32
     // rows (<= 128) whose P tile + accumulators fit next to the per-thread CDF/histogram
     NP = ((N + 3) / 4) * 4; if (NP > 32) NP = ((N + 7) / 8) * 8;
-    const int np2 = NP <= 4 ? 4 : NP <= 8 ? 8 : NP <= 16 ? 16 : NP <= 32 ? 32 : 64;
-    const size_t z_fixed = (size_t)np2 * ZT * sizeof(T) + (size_t)NP * ZT * sizeof(int);
     const size_t z_budget = NP <= 32 ? (size_t)112 * 1024 : (size_t)226 * 1024;
     KT = ((K + 31) / 32) * 32; if (KT > 128) KT = 128;
-    while (KT > 32 && z_fixed + (size_t)KT * (NP * sizeof(T) + N * sizeof(int)) > z_budget) KT -= 32;
-    z_smem = z_fixed + (size_t)KT * (NP * sizeof(T) + N * sizeof(int));
+    const int zw = NP <= 32 ? 8 : 4;
+    while (KT > 32 && zstat_smem_bytes<T>(KT, NP, N, zw) > z_budget) KT -= 32;
+    z_smem = zstat_smem_bytes<T>(KT, NP, N, zw);
     n_ktiles = (K + KT - 1) / KT;
     const int cts = (int)((G + 31) / 32);
-    d.n_zitems = cts * n_ktiles * ((KT + 31) / 32);
+    // rows per work item: fine enough that every warp gets several items (tail balance)
+    ZR = 32;
+    while (ZR > 1 && (long long)cts * ((K + ZR - 1) / ZR) < 16LL * 148 * 16) ZR >>= 1;
+    if (ZR > KT) ZR = KT;
+    d.n_zitems = cts * n_ktiles * ((KT + ZR - 1) / ZR);
     d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, 256);
     if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + 2 * N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
         dalloc(&d.red, PC_COLS) || dalloc(&work_ctr, n_ktiles + 8) || dalloc(&nanflags, 5 * N)) return 1;
-    if (dalloc(&d.ctrl, 1)) return 1;
+    if (dalloc(&d.ctrl, 1) || dalloc(&red_slices, RED_BLOCKS * PC_COLS) || dalloc(&red_ticket, 1)) return 1;
     d.metrics_cap = 256;
     if (dalloc(&d.metrics, (long long)d.metrics_cap * MC_COLS)) return 1;
     CK(cudaMallocHost((void**)&h_metrics, (size_t)d.metrics_cap * MC_COLS * sizeof(double)));
@@ -311,11 +315,12 @@ struct Sampler : bnmf_handle {
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device);
     int per_sm = NPV <= 32 ? 2 : 1;
     int bx = dev_sms * per_sm / n_ktiles; if (bx < 1) bx = 1;
-    const long long items = (long long)((d.G + 31) / 32) * ((KT + 31) / 32);
-    long long need = (items + (ZT / 32) - 1) / (ZT / 32);
+    const long long items = (long long)((d.G + 31) / 32) * ((KT + ZR - 1) / ZR);
+    constexpr int ZW = ZWarps<NPV>::value;
+    long long need = (items + ZW - 1) / ZW;
     if (bx > need) bx = (int)need;
     dim3 grid(bx, n_ktiles);
-    kern<<<grid, ZT, z_smem, stream>>>(d, KT, work_ctr);
+    kern<<<grid, 32 * ZW, z_smem, stream>>>(d, KT, ZR, work_ctr);
     return 0;
   }
   int z_dispatch(bool configure) {
@@ -475,7 +480,7 @@ struct Sampler : bnmf_handle {
   double* asum = nullptr; double sig_alpha = 3.0, sig_beta = 3.0;
 
   int finish_iteration() {
-    k_reduce_partials<T, 256><<<1, 256, 0, stream>>>(d); ++launches;
+    k_reduce_partials<T, 256><<<RED_BLOCKS, 256, 0, stream>>>(d, red_slices, red_ticket); ++launches;
     if (allreduce_red()) return 1;
     k_metrics<T><<<1, 32, 0, stream>>>(d); ++launches;
     return 0;

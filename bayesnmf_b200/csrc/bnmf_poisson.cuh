@@ -212,25 +212,33 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int from_prior, int
 // for free, the per-iteration metrics of R/utils.R:412-455 (log-likelihood, RMSE,
 // padded KL).
 //
-// Mapping: a warp owns a work item = 32 consecutive genomes (one per lane) x 32
-// consecutive mutation types; lanes walk down the 32 rows together.  Per lane the
-// column E[.,g] and the SE accumulators live in registers, the running CDF and the
-// per-cell pick histogram in a lane-private, bank-conflict-free slice of shared
-// memory ([n][thread]).  After each row the histogram is summed across the warp
-// with REDUX and added to a block-level SP table in shared memory; SE leaves the
-// SM once per item, SP once per block.  Items are handed out dynamically.
+// Mapping: a warp owns a work item = 32 consecutive genomes (one per lane) x ZR
+// consecutive mutation types and walks down the rows.  Per row:
+//   phase 1 (lane = cell)   the lane builds the running CDF of its cell in a warp-private
+//                           slice of shared memory ([cell][n], odd stride) and the metric
+//                           partials; E[.,g] and the SE accumulators stay in registers.
+//   phase 2 (lane = share)  counts per cell are heavy-tailed (max/mean ~ 4 over a warp), so
+//                           the picks of the 32 cells are cut into quads (4 picks = one
+//                           Philox block), laid end to end, and every lane takes an equal
+//                           contiguous share of the row's quads, whatever cells they belong
+//                           to.  A cell that starts inside a lane's share is counted by that
+//                           lane straight into the cell's histogram column (exclusive, no
+//                           atomics); the part of a cell that spills into following lanes
+//                           is counted in those lanes' private columns and folded in by a
+//                           short, conflict-free fix-up (lanes continuing the same cell take
+//                           turns).
+//   reduce                  REDUX sums the histogram columns across the warp into the
+//                           block-level SP table; each lane adds its own column to SE.
+// SE leaves the SM once per item, SP once per block.  Items are handed out dynamically.
 //
 // Arithmetic contract (what oracle/ restates bit-for-bit):
 //   p_n   = Pa[k,n] * E[n,g]            (Pa = P with excluded signatures zeroed)
 //   cdf_n = cdf_{n-1} + p_n              (sequential, no FMA)
-//   pick  = #{ n : cdf_n <= u * cdf_{N-1} },  u = (w + 0.5) 2^-32,
+//   pick  = min(#{ n : cdf_n <= u * cdf_{N-1} }, N-1),  u = (w + 0.5) 2^-32,
 //           w = word (j mod 4) of Philox block j/4 of stream (iter, PUR_Z, k + K*g)
 // ------------------------------------------------------------------------------
-constexpr int ZT = 256;  // threads per block of k_zstat
-
-template <int NP> struct NextPow2 {
-  static constexpr int value = NP <= 4 ? 4 : NP <= 8 ? 8 : NP <= 16 ? 16 : NP <= 32 ? 32 : 64;
-};
+// warps per block of k_zstat: 8 up to 32 signatures, 4 beyond (shared memory per warp doubles)
+template <int NP> struct ZWarps { static constexpr int value = NP <= 32 ? 8 : 4; };
 
 template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
 template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
@@ -239,19 +247,63 @@ template <typename T> __device__ __forceinline__ T add_rn(T a, T b);
 template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
 template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
 
+// #{ n < NP : col[n] <= t } for a non-decreasing column whose last entry is > t.
+// Two levels of independent loads (block pivots, then inside the block) instead of a
+// five-deep dependent binary search: the latency of a pick is two shared-memory round trips.
 template <typename T, int NP>
-__global__ void __launch_bounds__(ZT, (NP <= 32 ? 2 : 1))
-k_zstat(Dev<T> d, int KT, int* work_ctr) {
-  constexpr int NP2 = NextPow2<NP>::value;
+__device__ __forceinline__ int cdf_search(const T* col, T t) {
+  constexpr int S = NP <= 32 ? 4 : 8;
+  constexpr int NB = NP / S;
+  static_assert(NP % S == 0, "padded signature count must be a multiple of the search block");
+  int b = 0;
+#pragma unroll
+  for (int j = 0; j < NB - 1; ++j) b += (col[(j + 1) * S - 1] <= t) ? 1 : 0;
+  const T* blk = col + b * S;
+  int pos = b * S;
+#pragma unroll
+  for (int j = 0; j < S - 1; ++j) pos += (blk[j] <= t) ? 1 : 0;
+  return pos;
+}
+
+// u * tot with u = (w + 0.5) 2^-32 (exactly representable), one rounding.
+// double: 2^52 + w is exact in the mantissa, so (w + 0.5) needs no int->double conversion,
+// and the 2^-32 is folded into `tots` = tot * 2^-32 (exact for every normal tot >= 2^-990).
+__device__ __forceinline__ double pick_threshold(uint32_t w, double tot, double tots, bool scaled_ok) {
+  const double wp = __dadd_rn(__hiloint2double(0x43300000, (int)w), -4503599627370495.5);   // w + 0.5
+  return scaled_ok ? __dmul_rn(wp, tots) : __dmul_rn(__dmul_rn(wp, 2.3283064365386963e-10), tot);
+}
+__device__ __forceinline__ float pick_threshold(uint32_t w, float tot, float, bool) {
+  return __fmul_rn(u01<float>(w), tot);
+}
+
+// shared memory of k_zstat in bytes, for a K tile of KT rows (host and device agree on it)
+template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int KT, int NP, int N, int W) {
+  return (size_t)KT * NP * sizeof(T) + (size_t)W * 32 * (NP + 1) * sizeof(T) + (size_t)W * NP * 32 * 2 * sizeof(int) +
+         (size_t)W * 68 * sizeof(int) + (size_t)KT * N * sizeof(int);
+}
+
+template <typename T, int NP>
+__global__ void __launch_bounds__(32 * ZWarps<NP>::value, (NP <= 32 ? 2 : 1))
+k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
+  constexpr int W = ZWarps<NP>::value;
+  constexpr int ZT = 32 * W;
+  constexpr int NPS = NP + 1;                                        // odd stride: conflict-free columns
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = d.K, N = d.N, G = d.G;
-  T* Psm = reinterpret_cast<T*>(smem_raw);                 // [KT][NP]
-  T* cdf = Psm + (size_t)KT * NP;                          // [NP2][ZT]
-  int* hist = reinterpret_cast<int*>(cdf + (size_t)NP2 * ZT);  // [NP][ZT]
-  int* spacc = hist + (size_t)NP * ZT;                     // [KT][N]
-  __shared__ int s_item[ZT / 32];
+  T* Psm = reinterpret_cast<T*>(smem_raw);                          // [KT][NP]
+  T* cdf_all = Psm + (size_t)KT * NP;                               // [W][32 cells][NPS]
+  int* hist_all = reinterpret_cast<int*>(cdf_all + (size_t)W * 32 * NPS);  // [W][NP][32 cells]
+  int* cont_all = hist_all + (size_t)W * NP * 32;                   // [W][NP][32 lanes]
+  int* own_all = cont_all + (size_t)W * NP * 32;                    // [W][33 + 32 (+pad)]
+  int* spacc = own_all + (size_t)W * 68;                            // [KT][N]
+  __shared__ int s_item[W];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  T* cdf = cdf_all + (size_t)wid * 32 * NPS;
+  int* hist = hist_all + (size_t)wid * NP * 32;
+  int* cont = cont_all + (size_t)wid * NP * 32;
+  int* s_excl = own_all + wid * 68;              // [33] first quad of each cell (+ total)
+  int* s_m = s_excl + 34;                        // [32] picks of each cell
   const int ky = blockIdx.y;            // k-tile
   const int k0 = ky * KT;
   const int krows = min(KT, K - k0);
@@ -265,14 +317,15 @@ k_zstat(Dev<T> d, int KT, int* work_ctr) {
     Psm[i] = v;
   }
   for (int i = tid; i < KT * N; i += ZT) spacc[i] = 0;
-  for (int n = 0; n < NP; ++n) hist[n * ZT + tid] = 0;
-  for (int n = NP; n < NP2; ++n) cdf[n * ZT + tid] = (T)INFINITY;
+#pragma unroll
+  for (int n = 0; n < NP; ++n) { hist[n * 32 + lane] = 0; cont[n * 32 + lane] = 0; }
   __syncthreads();
 
-  const int rts = (krows + 31) / 32;                 // row sub-tiles in this k-tile
+  const int rts = (krows + ZR - 1) / ZR;             // row sub-tiles in this k-tile
   const int cts = (G + 31) / 32;                     // column tiles
   const int n_items = rts * cts;
-  const int rts_all = ((d.K + KT - 1) / KT) * ((KT + 31) / 32);  // item id stride (for zpart)
+  const int rt_tile = (KT + ZR - 1) / ZR;
+  const int rts_all = ((d.K + KT - 1) / KT) * rt_tile;           // item id stride (for zpart)
 
   for (;;) {
     if (lane == 0) s_item[wid] = atomicAdd(&work_ctr[ky], 1);
@@ -283,7 +336,7 @@ k_zstat(Dev<T> d, int KT, int* work_ctr) {
     const int ct = item / rts, rt = item - ct * rts;
     const int g = ct * 32 + lane;
     const bool valid = g < G;
-    const long long gg = d.g0 + g;
+    const unsigned long long cell0 = (unsigned long long)K * (unsigned long long)(d.g0 + (long long)ct * 32);
 
     T Ereg[NP];
     int se[NP];
@@ -294,17 +347,17 @@ k_zstat(Dev<T> d, int KT, int* work_ctr) {
     }
     double a_sse = 0.0, a_kl = 0.0, a_ll = 0.0;
 
-    const int kk_end = min(32, krows - rt * 32);
+    const int kk_end = min(ZR, krows - rt * ZR);
     for (int r = 0; r < kk_end; ++r) {
-      const int kk = rt * 32 + r;
+      const int kk = rt * ZR + r;
       const int k = k0 + kk;
       const int m = valid ? d.Mi[(long long)k + (long long)K * g] : 0;
-      // running CDF
+      // ---- phase 1: running CDF of this lane's cell ----
       T acc = (T)0;
 #pragma unroll
       for (int n = 0; n < NP; ++n) {
         acc = add_rn<T>(acc, mul_rn<T>(Psm[kk * NP + n], Ereg[n]));
-        cdf[n * ZT + tid] = acc;
+        cdf[lane * NPS + n] = acc;
       }
       const T total = acc;
       if (valid) {
@@ -318,41 +371,116 @@ k_zstat(Dev<T> d, int KT, int* work_ctr) {
         a_sse += diff * diff;
       }
       const bool work = (m > 0) && (total > (T)0);
-      if (__any_sync(0xffffffffu, work)) {
-        if (work) {
-          const Stream s = make_stream(d.seed, iter, PUR_Z, (unsigned long long)k + (unsigned long long)K * gg);
-          for (int j = 0; j < m; j += 4) {
-            const U4 w = s.at((uint32_t)(j >> 2));
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-            const int lim = min(4, m - j);
+      if (!__any_sync(0xffffffffu, work)) continue;
+      // quads of this lane's cell and their offsets in the row's flattened quad list
+      const int q = work ? (int)(((unsigned)m + 3u) >> 2) : 0;
+      int incl = q;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q < lim) {
-                const T t = mul_rn<T>(u01<T>(ww[q]), total);
-                int pos = 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int excl = incl - q;
+      const int Tq = __shfl_sync(0xffffffffu, incl, 31);
+      s_excl[lane] = excl; s_m[lane] = m;
+      if (lane == 31) s_excl[32] = Tq;
+      __syncwarp();   // CDF columns and the cell table visible to the whole warp
+      // ---- phase 2: an equal contiguous share [qd, qhi) of the row's quads per lane ----
+      int qd = (int)(((unsigned long long)lane * (unsigned)Tq) >> 5);
+      const int qhi = (int)(((unsigned long long)(lane + 1) * (unsigned)Tq) >> 5);
+      // owner of the first quad: the cell c with excl[c] <= qd < excl[c] + q[c]
+      int c = 0, ec = 0;
 #pragma unroll
-                for (int st = NP2 / 2; st > 0; st >>= 1)
-                  if (cdf[(pos + st - 1) * ZT + tid] <= t) pos += st;
-                if (pos > NP - 1) pos = NP - 1;   // unreachable for finite totals
-                hist[pos * ZT + tid] += 1;
-              }
+      for (int st = 16; st > 0; st >>= 1) {
+        const int e = __shfl_sync(0xffffffffu, excl, c + st);
+        if (e <= qd) { c += st; ec = e; }
+      }
+      int mc = __shfl_sync(0xffffffffu, m, c);
+      const int c_first = c;
+      const bool F = ec < qd;                      // the first cell started in an earlier lane's share
+      {
+        int nxt = ec + (int)(((unsigned)mc + 3u) >> 2);
+        const T* col = cdf + c * NPS;
+        int* tgt = F ? cont + lane : hist + c;
+        T tot = col[NP - 1];
+        T tots = tot * (T)2.3283064365386963e-10;
+        bool sok = tot >= (T)1e-290;
+        unsigned long long cell = cell0 + (unsigned long long)k + (unsigned long long)K * (unsigned)c;
+        for (; qd < qhi; ++qd) {
+          if (qd >= nxt) {          // next cell that has picks; it starts inside this share
+            do { ++c; ec = s_excl[c]; nxt = s_excl[c + 1]; } while (nxt == ec);
+            mc = s_m[c];
+            col = cdf + c * NPS;
+            tgt = hist + c;
+            tot = col[NP - 1];
+            tots = tot * (T)2.3283064365386963e-10;
+            sok = tot >= (T)1e-290;
+            cell = cell0 + (unsigned long long)k + (unsigned long long)K * (unsigned)c;
+          }
+          const int sub = qd - ec;
+          const int lim = mc - 4 * sub;              // picks in this quad: min(4, lim) >= 1
+          const U4 w = make_stream(d.seed, iter, PUR_Z, cell).at((uint32_t)sub);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+          int pp[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            pp[p] = 0;
+            if (p < lim) {
+              const T t = pick_threshold(ww[p], tot, tots, sok);
+              pp[p] = min(cdf_search<T, NP>(col, t), N - 1);   // the min is a no-op in fp64 (t < total)
+            }
+          }
+          // fold equal picks so that the four read-modify-writes hit distinct addresses
+          bool a1 = lim > 1, a2 = lim > 2, a3 = lim > 3;
+          int i0 = 1, i1 = 1, i2 = 1;
+          if (a1 && pp[1] == pp[0]) { i0 += 1; a1 = false; }
+          if (a2 && pp[2] == pp[0]) { i0 += 1; a2 = false; }
+          if (a3 && pp[3] == pp[0]) { i0 += 1; a3 = false; }
+          if (a2 && a1 && pp[2] == pp[1]) { i1 += 1; a2 = false; }
+          if (a3 && a1 && pp[3] == pp[1]) { i1 += 1; a3 = false; }
+          if (a3 && a2 && pp[3] == pp[2]) { i2 += 1; a3 = false; }
+          const int v0 = tgt[pp[0] * 32], v1 = tgt[pp[1] * 32], v2 = tgt[pp[2] * 32], v3 = tgt[pp[3] * 32];
+          tgt[pp[0] * 32] = v0 + i0;
+          if (a1) tgt[pp[1] * 32] = v1 + i1;
+          if (a2) tgt[pp[2] * 32] = v2 + i2;
+          if (a3) tgt[pp[3] * 32] = v3 + 1;
+        }
+      }
+      // ---- fix-up: lanes whose share began inside a cell hand their counts to its column,
+      //      one lane per cell at a time (lanes continuing the same cell are consecutive) ----
+      {
+        const unsigned fm = __ballot_sync(0xffffffffu, F);
+        const int cprev = __shfl_up_sync(0xffffffffu, c_first, 1);
+        const bool chain = F && lane > 0 && ((fm >> (lane - 1)) & 1u) && cprev == c_first;
+        const unsigned bm = __ballot_sync(0xffffffffu, chain);
+        const unsigned x = ~bm & (0xffffffffu >> (31 - lane));     // lanes <= me that do not chain (lane 0 never does)
+        const int turn = F ? 1 + lane - (31 - __clz(x)) : 0;
+        const int turns = __reduce_max_sync(0xffffffffu, turn);
+        for (int j = 1; j <= turns; ++j) {
+          __syncwarp();
+          if (turn == j) {
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+              const int v = cont[n * 32 + lane];
+              if (v) { hist[n * 32 + c_first] += v; cont[n * 32 + lane] = 0; }
             }
           }
         }
         __syncwarp();
-        int mytot0 = 0, mytot1 = 0;
-#pragma unroll
-        for (int n = 0; n < NP; ++n) {
-          const int v = hist[n * ZT + tid];
-          hist[n * ZT + tid] = 0;
-          se[n] += v;
-          const int tot = __reduce_add_sync(0xffffffffu, v);
-          if (n < 32) { if (lane == n) mytot0 = tot; }
-          else        { if (lane == n - 32) mytot1 = tot; }
-        }
-        if (lane < N && mytot0) atomicAdd(&spacc[kk * N + lane], mytot0);
-        if (NP > 32 && lane + 32 < N && mytot1) atomicAdd(&spacc[kk * N + lane + 32], mytot1);
       }
+      int mytot0 = 0, mytot1 = 0;
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const int v = hist[n * 32 + lane];
+        hist[n * 32 + lane] = 0;
+        se[n] += v;
+        const int tot = __reduce_add_sync(0xffffffffu, v);
+        if (n < 32) { if (lane == n) mytot0 = tot; }
+        else        { if (lane == n - 32) mytot1 = tot; }
+      }
+      if (lane < N && mytot0) atomicAdd(&spacc[kk * N + lane], mytot0);
+      if (NP > 32 && lane + 32 < N && mytot1) atomicAdd(&spacc[kk * N + lane + 32], mytot1);
+      __syncwarp();   // the CDF columns are rewritten by the next row
     }
     // SE leaves the SM once per item
     if (valid) {
@@ -363,7 +491,7 @@ k_zstat(Dev<T> d, int KT, int* work_ctr) {
     // per-item metric partials, fixed reduction order
     a_sse = warp_sum(a_sse); a_kl = warp_sum(a_kl); a_ll = warp_sum(a_ll);
     if (lane == 0) {
-      const long long gi = (long long)ct * rts_all + (long long)ky * ((KT + 31) / 32) + rt;
+      const long long gi = (long long)ct * rts_all + (long long)ky * rt_tile + rt;
       double* zp = d.zpart + gi * PC_COLS;
       zp[PC_SSE] = a_sse; zp[PC_KLV] = a_kl; zp[PC_LLV] = a_ll; zp[PC_LP_E] = 0.0; zp[PC_EACC] = 0.0;
     }
@@ -379,28 +507,47 @@ k_zstat(Dev<T> d, int KT, int* work_ctr) {
 }
 
 // ------------------------------------------------------------------------------
-// k_reduce_partials: fold per-item / per-block partials in a fixed order (one block).
+// k_reduce_partials: fold per-item / per-block partials in a fixed order.
 // red[c] = sum_items zpart[.][c] + sum_blocks epart[.][c]  (+ data constants)
-// lp_P   = sum_n zpart[n_zitems + n]   (slots written by k_pside)
+// lp_P   = sum_n zpart[n_zitems + n]   (slots written by k_pside / k_pprior)
+// RED_BLOCKS blocks each fold a fixed contiguous slice; the last one to finish (ticket)
+// folds the slices in index order, so the result does not depend on scheduling.
 // ------------------------------------------------------------------------------
+constexpr int RED_BLOCKS = 64;
 template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_reduce_partials(Dev<T> d) {
+__global__ void __launch_bounds__(THREADS) k_reduce_partials(Dev<T> d, double* slices /*[RED_BLOCKS][PC_COLS]*/, unsigned* ticket) {
   __shared__ double scratch[THREADS / 32];
+  __shared__ bool last;
+  const long long total = (long long)d.n_zitems + d.n_eblocks;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long lo = per * blockIdx.x, hi = lo + per < total ? lo + per : total;
   for (int c = 0; c < PC_COLS; ++c) {
     double v = 0.0;
-    for (int i = threadIdx.x; i < d.n_zitems; i += THREADS) v += d.zpart[(long long)i * PC_COLS + c];
-    for (int i = threadIdx.x; i < d.n_eblocks; i += THREADS) v += d.epart[(long long)i * PC_COLS + c];
-    double s = block_sum<THREADS>(v, scratch);
-    if (threadIdx.x == 0) {
-      if (c == PC_LLV) s += d.ll_const;
-      if (c == PC_KLV) s += d.kl_const;
-      d.red[c] = s;
-    }
+    for (long long i = lo + threadIdx.x; i < hi; i += THREADS)
+      v += i < d.n_zitems ? d.zpart[i * PC_COLS + c] : d.epart[(i - d.n_zitems) * PC_COLS + c];
+    const double s = block_sum<THREADS>(v, scratch);
+    if (threadIdx.x == 0) slices[blockIdx.x * PC_COLS + c] = s;
   }
-  double v = 0.0;
-  for (int i = threadIdx.x; i < d.N; i += THREADS) v += d.zpart[(long long)d.n_zitems * PC_COLS + i];
-  double s = block_sum<THREADS>(v, scratch);
-  if (threadIdx.x == 0) *d.lp_P = s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < PC_COLS) {
+    const int c = threadIdx.x;
+    double s = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += ((volatile double*)slices)[b * PC_COLS + c];
+    if (c == PC_LLV) s += d.ll_const;
+    if (c == PC_KLV) s += d.kl_const;
+    d.red[c] = s;
+  }
+  if (threadIdx.x == 32) {
+    double s = 0.0;
+    for (int i = 0; i < d.N; ++i) s += d.zpart[(long long)d.n_zitems * PC_COLS + i];
+    *d.lp_P = s;
+    *ticket = 0u;
+  }
 }
 
 // ------------------------------------------------------------------------------
