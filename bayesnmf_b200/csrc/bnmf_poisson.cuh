@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int from_prior, int
 // Arithmetic contract (what oracle/ restates bit-for-bit):
 //   p_n   = Pa[k,n] * E[n,g]            (Pa = P with excluded signatures zeroed)
 //   cdf_n = cdf_{n-1} + p_n              (sequential, no FMA)
-//   pick  = min(#{ n : cdf_n <= u * cdf_{N-1} }, N-1),  u = (w + 0.5) 2^-32,
+//   pick  = min(#{ n : cdf_n <= t }, N-1),  t = (w + 0.5) * (cdf_{N-1} * 2^-32)
+//           [float state: t = ((w >> 8) + 0.5) * (cdf_{N-1} * 2^-24)],
 //           w = word (j mod 4) of Philox block j/4 of stream (iter, PUR_Z, k + K*g)
 // ------------------------------------------------------------------------------
 // warps per block of k_zstat: 8 up to 32 signatures, 4 beyond (shared memory per warp doubles)
@@ -265,15 +266,47 @@ __device__ __forceinline__ int cdf_search(const T* col, T t) {
   return pos;
 }
 
-// u * tot with u = (w + 0.5) 2^-32 (exactly representable), one rounding.
-// double: 2^52 + w is exact in the mantissa, so (w + 0.5) needs no int->double conversion,
-// and the 2^-32 is folded into `tots` = tot * 2^-32 (exact for every normal tot >= 2^-990).
-__device__ __forceinline__ double pick_threshold(uint32_t w, double tot, double tots, bool scaled_ok) {
+// Pick threshold t = (w + 0.5) * tots with tots = total * 2^-32 (one rounding each; the same
+// value as u * total, u = (w + 0.5) 2^-32, whenever tots is a normal number).
+// double: 2^52 + w is exact in the mantissa, so w + 0.5 needs no int->double conversion.
+__device__ __forceinline__ double pick_threshold(uint32_t w, double tots) {
   const double wp = __dadd_rn(__hiloint2double(0x43300000, (int)w), -4503599627370495.5);   // w + 0.5
-  return scaled_ok ? __dmul_rn(wp, tots) : __dmul_rn(__dmul_rn(wp, 2.3283064365386963e-10), tot);
+  return __dmul_rn(wp, tots);
 }
-__device__ __forceinline__ float pick_threshold(uint32_t w, float tot, float, bool) {
-  return __fmul_rn(u01<float>(w), tot);
+// float: 24 random bits, t = ((w >> 8) + 0.5) * (total * 2^-24)
+__device__ __forceinline__ float pick_threshold(uint32_t w, float tots) {
+  return __fmul_rn((float)(w >> 8) + 0.5f, tots);
+}
+template <typename T> __device__ __forceinline__ T pick_scale(T total);
+template <> __device__ __forceinline__ double pick_scale<double>(double total) { return __dmul_rn(total, 2.3283064365386963e-10); }
+template <> __device__ __forceinline__ float pick_scale<float>(float total) { return __fmul_rn(total, 5.9604644775390625e-8f); }
+
+// One quad: four thresholds from one Philox block, four searches, and the histogram update.
+// Equal picks are folded first so that the four read-modify-writes hit distinct addresses and
+// their loads can all be in flight together.  `lim` = picks of the cell still to draw (>= 1);
+// with ALL4 the four searches are straight-line code (no branches) whatever `lim`.
+template <typename T, int NP, bool ALL4>
+__device__ __forceinline__ void zstat_quad(const U4& w, const T* col, T tots, int lim, int N, int* tgt) {
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  int pp[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    pp[p] = 0;
+    if (ALL4 || p < lim) pp[p] = min(cdf_search<T, NP>(col, pick_threshold(ww[p], tots)), N - 1);
+  }
+  bool a1 = lim > 1, a2 = lim > 2, a3 = lim > 3;
+  int i0 = 1, i1 = 1, i2 = 1;
+  if (a1 && pp[1] == pp[0]) { i0 += 1; a1 = false; }
+  if (a2 && pp[2] == pp[0]) { i0 += 1; a2 = false; }
+  if (a3 && pp[3] == pp[0]) { i0 += 1; a3 = false; }
+  if (a2 && a1 && pp[2] == pp[1]) { i1 += 1; a2 = false; }
+  if (a3 && a1 && pp[3] == pp[1]) { i1 += 1; a3 = false; }
+  if (a3 && a2 && pp[3] == pp[2]) { i2 += 1; a3 = false; }
+  const int v0 = tgt[pp[0] * 32], v1 = tgt[pp[1] * 32], v2 = tgt[pp[2] * 32], v3 = tgt[pp[3] * 32];
+  tgt[pp[0] * 32] = v0 + i0;
+  if (a1) tgt[pp[1] * 32] = v1 + i1;
+  if (a2) tgt[pp[2] * 32] = v2 + i2;
+  if (a3) tgt[pp[3] * 32] = v3 + 1;
 }
 
 // shared memory of k_zstat in bytes, for a K tile of KT rows (host and device agree on it)
@@ -402,48 +435,23 @@ k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
         int nxt = ec + (int)(((unsigned)mc + 3u) >> 2);
         const T* col = cdf + c * NPS;
         int* tgt = F ? cont + lane : hist + c;
-        T tot = col[NP - 1];
-        T tots = tot * (T)2.3283064365386963e-10;
-        bool sok = tot >= (T)1e-290;
+        T tots = pick_scale<T>(col[NP - 1]);
         unsigned long long cell = cell0 + (unsigned long long)k + (unsigned long long)K * (unsigned)c;
+        const bool dense = Tq >= 96;               // rows of mostly full quads: branch-free searches
         for (; qd < qhi; ++qd) {
           if (qd >= nxt) {          // next cell that has picks; it starts inside this share
             do { ++c; ec = s_excl[c]; nxt = s_excl[c + 1]; } while (nxt == ec);
             mc = s_m[c];
             col = cdf + c * NPS;
             tgt = hist + c;
-            tot = col[NP - 1];
-            tots = tot * (T)2.3283064365386963e-10;
-            sok = tot >= (T)1e-290;
+            tots = pick_scale<T>(col[NP - 1]);
             cell = cell0 + (unsigned long long)k + (unsigned long long)K * (unsigned)c;
           }
           const int sub = qd - ec;
           const int lim = mc - 4 * sub;              // picks in this quad: min(4, lim) >= 1
           const U4 w = make_stream(d.seed, iter, PUR_Z, cell).at((uint32_t)sub);
-          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-          int pp[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            pp[p] = 0;
-            if (p < lim) {
-              const T t = pick_threshold(ww[p], tot, tots, sok);
-              pp[p] = min(cdf_search<T, NP>(col, t), N - 1);   // the min is a no-op in fp64 (t < total)
-            }
-          }
-          // fold equal picks so that the four read-modify-writes hit distinct addresses
-          bool a1 = lim > 1, a2 = lim > 2, a3 = lim > 3;
-          int i0 = 1, i1 = 1, i2 = 1;
-          if (a1 && pp[1] == pp[0]) { i0 += 1; a1 = false; }
-          if (a2 && pp[2] == pp[0]) { i0 += 1; a2 = false; }
-          if (a3 && pp[3] == pp[0]) { i0 += 1; a3 = false; }
-          if (a2 && a1 && pp[2] == pp[1]) { i1 += 1; a2 = false; }
-          if (a3 && a1 && pp[3] == pp[1]) { i1 += 1; a3 = false; }
-          if (a3 && a2 && pp[3] == pp[2]) { i2 += 1; a3 = false; }
-          const int v0 = tgt[pp[0] * 32], v1 = tgt[pp[1] * 32], v2 = tgt[pp[2] * 32], v3 = tgt[pp[3] * 32];
-          tgt[pp[0] * 32] = v0 + i0;
-          if (a1) tgt[pp[1] * 32] = v1 + i1;
-          if (a2) tgt[pp[2] * 32] = v2 + i2;
-          if (a3) tgt[pp[3] * 32] = v3 + 1;
+          if (dense) zstat_quad<T, NP, true>(w, col, tots, lim, N, tgt);
+          else       zstat_quad<T, NP, false>(w, col, tots, lim, N, tgt);
         }
       }
       // ---- fix-up: lanes whose share began inside a cell hand their counts to its column,

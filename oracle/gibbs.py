@@ -107,7 +107,7 @@ def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_
     rmultinom(1, size = M[k,g], prob = probs/sum(probs))  (R/sample_params.R:253-265).
     rmultinom is a chain of conditional binomials; a multinomial is equally the
     histogram of M[k,g] independent categorical draws, which is what is used here
-    (fp64 inverse CDF; pick = #{n : cdf_n <= u * cdf_N})."""
+    (fp64 inverse CDF; pick = #{n : cdf_n <= u * cdf_N}, u = (w + 0.5) 2^-32)."""
     M = np.asarray(M)
     K, G = M.shape
     N = P.shape[1]
@@ -137,8 +137,12 @@ def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_
         w = px.words(seed, it, px.PUR_Z, cell_id[owner], j >> 2)
         W = np.stack(w, axis=0)
         word = W[j & 3, np.arange(len(owner))]
-        u = px.u01(word, bits)
-        t = u * total[kk[owner], gg[owner]]
+        # t = (w + 0.5) * (total * 2^-32): the same number as u01(w) * total (power-of-two
+        # scaling is exact), written the way the kernel evaluates it
+        if bits == 32:
+            t = (word.astype(np.float64) + 0.5) * (total[kk[owner], gg[owner]] * 2.0 ** -32)
+        else:
+            t = ((word >> np.uint32(8)).astype(np.float64) + 0.5) * (total[kk[owner], gg[owner]] * 2.0 ** -24)
         cd = cdf[kk[owner], :, gg[owner]]          # picks x N
         pick = (cd <= t[:, None]).sum(axis=1)
         pick = np.minimum(pick, N - 1)
