@@ -247,7 +247,7 @@ BNMF_HD double seg_inv(double s, double a, double b, double q) {
 BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, double X) {
   const double LO = 1e-3, HI = 1e4;
   AlphaTarget t; t.cm1 = C - 1.0; t.b = D - log(beta) - log(X);
-  // --- mode by safeguarded Newton on h' (strictly decreasing), 16 fixed steps ---
+  // --- mode by safeguarded Newton on h' (strictly decreasing), at most 16 steps ---
   double m;
   if (alpha_hp(t, LO) <= 0.0) m = LO;
   else if (alpha_hp(t, HI) >= 0.0) m = HI;
@@ -259,7 +259,7 @@ BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, dou
       double f = alpha_hp(t, x);
       if (f > 0.0) a = x; else b = x;
       double xn = x - f / alpha_hpp(t, x);
-      if (fabs(xn - x) <= 1e-10 * x) xn = x;            // converged: freeze
+      if (fabs(xn - x) <= 1e-10 * x) break;             // converged: every later step would leave x unchanged
       else if (!(xn > a && xn < b)) xn = sqrt(a * b);   // safeguard: geometric bisection
       x = xn;
     }
