@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int from_prior, int
         be = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_P1, c),
                                 (double)d.A_p.at(c) + al, (double)d.B_p.at(c) + Pold);
         al = alpha_draw(make_stream(d.seed, iter, PUR_HYP_P2, c),
-                        (double)d.C_p.at(c), (double)d.D_p.at(c), be, Pold);
+                        (double)d.C_p.at(c), (double)d.D_p.at(c), be, Pold, al);
         d.Beta_p[c] = (T)be; d.Alpha_p[c] = (T)al;
       }
       if (!keepP) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int from_prior, int
         be = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
                                 (double)d.A_e.at(idx) + al, (double)d.B_e.at(idx) + Eold);
         al = alpha_draw(make_stream(d.seed, iter, PUR_HYP_E2, c),
-                        (double)d.C_e.at(idx), (double)d.D_e.at(idx), be, Eold);
+                        (double)d.C_e.at(idx), (double)d.D_e.at(idx), be, Eold, al);
         d.Beta_e[idx] = (T)be; d.Alpha_e[idx] = (T)al;
       }
       if (!keepE) {

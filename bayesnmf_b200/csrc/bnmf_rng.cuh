@@ -193,23 +193,27 @@ template <typename T> BNMF_HD T truncnorm0_draw(const Stream& s, T mean, T sd) {
 }
 
 // ---- digamma / trigamma (recurrence to x >= 6, then asymptotic series) ----------
-template <typename T> BNMF_HD T digamma(T x) {
-  T r = (T)0;
-  while (x < (T)6) { r = r - (T)1 / x; x = x + (T)1; }
-  T f = (T)1 / (x * x);
-  T t = f * ((T)(-1.0 / 12.0) + f * ((T)(1.0 / 120.0) + f * ((T)(-1.0 / 252.0) +
-        f * ((T)(1.0 / 240.0) + f * (T)(-1.0 / 132.0)))));
-  return r + tlog<T>(x) - (T)0.5 / x + t;
+// Evaluated together: the Newton step on h' needs both and they share every reciprocal.
+template <typename T> BNMF_HD void digamma_trigamma(T x, T& psi, T& tri) {
+  T r1 = (T)0, r2 = (T)0;
+  while (x < (T)6) {
+    const T inv = (T)1 / x;
+    r1 = r1 - inv;
+    r2 = r2 + inv * inv;
+    x = x + (T)1;
+  }
+  const T inv = (T)1 / x;
+  const T f = inv * inv;
+  const T t1 = f * ((T)(-1.0 / 12.0) + f * ((T)(1.0 / 120.0) + f * ((T)(-1.0 / 252.0) +
+               f * ((T)(1.0 / 240.0) + f * (T)(-1.0 / 132.0)))));
+  psi = r1 + tlog<T>(x) - (T)0.5 * inv + t1;
+  const T t2 = inv + (T)0.5 * f +
+               (f * inv) * ((T)(1.0 / 6.0) + f * ((T)(-1.0 / 30.0) + f * ((T)(1.0 / 42.0) +
+               f * (T)(-1.0 / 30.0))));
+  tri = r2 + t2;
 }
-template <typename T> BNMF_HD T trigamma(T x) {
-  T r = (T)0;
-  while (x < (T)6) { r = r + (T)1 / (x * x); x = x + (T)1; }
-  T f = (T)1 / (x * x);
-  T t = (T)1 / x + (T)0.5 * f +
-        (f / x) * ((T)(1.0 / 6.0) + f * ((T)(-1.0 / 30.0) + f * ((T)(1.0 / 42.0) +
-        f * (T)(-1.0 / 30.0))));
-  return r + t;
-}
+template <typename T> BNMF_HD T digamma(T x) { T p, t; digamma_trigamma<T>(x, p, t); return p; }
+template <typename T> BNMF_HD T trigamma(T x) { T p, t; digamma_trigamma<T>(x, p, t); return t; }
 
 // ---- shape parameter of the Gamma prior --------------------------------------
 // The reference draws Alpha[.] with armspp::arms(n_samples = 1, log_pdf, 1e-3, 1e4)
@@ -225,17 +229,21 @@ struct AlphaTarget { double cm1, b; };
 BNMF_HD double alpha_h(const AlphaTarget& t, double x) { return t.cm1 * log(x) - t.b * x - lgamma(x); }
 BNMF_HD double alpha_hp(const AlphaTarget& t, double x) { return t.cm1 / x - t.b - digamma<double>(x); }
 BNMF_HD double alpha_hpp(const AlphaTarget& t, double x) { return -t.cm1 / (x * x) - trigamma<double>(x); }
-
-// integral of exp(s*(x - x0)) over [a, b], a <= b, anchored at the end with the larger
-// exponent so that expm1 only ever sees a non-positive argument (no overflow).
-BNMF_HD double seg_mass(double s, double a, double b, double x0) {
-  double w = b - a;
-  double sw = s * w;
-  if (fabs(sw) < 1e-8) return exp(s * (a - x0)) * w * (1.0 + 0.5 * sw);
-  if (sw > 0.0) return exp(s * (b - x0)) * expm1(-sw) / (-s);
-  return exp(s * (a - x0)) * expm1(sw) / s;
+BNMF_HD void alpha_hp_hpp(const AlphaTarget& t, double x, double& f, double& fp) {
+  double psi, tri;
+  digamma_trigamma<double>(x, psi, tri);
+  f = t.cm1 / x - t.b - psi;
+  fp = -t.cm1 / (x * x) - tri;
 }
-// inverse of the above: x in [a,b] with partial mass fraction q in (0,1).
+
+// integral of exp(-|s| y) over [0, w]: the mass of a linear-exponent segment of width w
+// relative to its higher end (never overflows).
+BNMF_HD double seg_unit(double s, double w) {
+  const double sw = fabs(s) * w;
+  if (sw < 1e-8) return w * (1.0 - 0.5 * sw);
+  return -expm1(-sw) / fabs(s);
+}
+// x in [a,b] with partial mass fraction q in (0,1) of the segment exp(s x) over [a,b].
 BNMF_HD double seg_inv(double s, double a, double b, double q) {
   double w = b - a;
   double sw = s * w;
@@ -244,28 +252,43 @@ BNMF_HD double seg_inv(double s, double a, double b, double q) {
   return a + log1p(q * expm1(sw)) / s;
 }
 
-BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, double X) {
+// digamma(1e-3), digamma(1e4): the two end-point tests of the mode search, as literals so that
+// the oracle, the host check and the kernels decide them identically
+#define BNMF_PSI_LO (-1000.5755719318103)
+#define BNMF_PSI_HI (9.21029037114285)
+#define BNMF_ALPHA_NEWTON 16
+#define BNMF_ALPHA_TOL 1e-2
+
+// x0 = where the search for the mode starts: the current value of Alpha (a draw from this
+// very conditional one sweep ago, hence within about one standard deviation of the mode).
+// The mode is only needed approximately: any three increasing tangent points give a valid
+// envelope of a concave log-density, their position only moves the acceptance rate.
+BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, double X, double x0) {
   const double LO = 1e-3, HI = 1e4;
   AlphaTarget t; t.cm1 = C - 1.0; t.b = D - log(beta) - log(X);
-  // --- mode by safeguarded Newton on h' (strictly decreasing), at most 16 steps ---
+  // --- approximate mode: safeguarded Newton on h' (strictly decreasing) to BNMF_ALPHA_TOL ---
   double m;
-  if (alpha_hp(t, LO) <= 0.0) m = LO;
-  else if (alpha_hp(t, HI) >= 0.0) m = HI;
+  if (t.cm1 / LO - t.b - BNMF_PSI_LO <= 0.0) m = LO;
+  else if (t.cm1 / HI - t.b - BNMF_PSI_HI >= 0.0) m = HI;
   else {
     double a = LO, b = HI;
-    double x = C > 1.0 ? C : 1.0;   // crude start
-    if (x >= HI) x = 0.5 * HI;
-    for (int it = 0; it < 16; ++it) {
-      double f = alpha_hp(t, x);
+    double x = x0;
+    if (!(x > LO && x < HI)) x = C > 1.0 ? (C < HI ? C : 0.5 * HI) : 1.0;
+    for (int it = 0; it < BNMF_ALPHA_NEWTON; ++it) {
+      double f, fp;
+      alpha_hp_hpp(t, x, f, fp);
       if (f > 0.0) a = x; else b = x;
-      double xn = x - f / alpha_hpp(t, x);
-      if (fabs(xn - x) <= 1e-10 * x) break;             // converged: every later step would leave x unchanged
-      else if (!(xn > a && xn < b)) xn = sqrt(a * b);   // safeguard: geometric bisection
+      double xn = x * exp(-f / (x * fp));               // Newton step in log x (h' is close to linear in it)
+      if (!(xn > a && xn < b)) xn = sqrt(a * b);        // safeguard: geometric bisection
+      const bool conv = fabs(xn - x) <= BNMF_ALPHA_TOL * x;
       x = xn;
+      if (conv) break;
     }
     m = x;
   }
-  double s = 1.0 / sqrt(-alpha_hpp(t, m));
+  double hp_m, hpp_m;
+  alpha_hp_hpp(t, m, hp_m, hpp_m);
+  double s = 1.0 / sqrt(-hpp_m);
   // --- three tangent points inside (0, inf), strictly increasing ---
   double xs[3];
   xs[1] = m;
@@ -274,7 +297,10 @@ BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, dou
   if (m <= LO) { xs[0] = LO; xs[1] = LO + s; xs[2] = LO + 2.0 * s; }
   if (m >= HI) { xs[2] = HI; xs[1] = HI - s; xs[0] = HI - 2.0 * s; if (xs[0] < 0.5 * HI) { xs[0] = 0.5 * HI; xs[1] = 0.75 * HI; } }
   double hv[3], sl[3];
-  for (int j = 0; j < 3; ++j) { hv[j] = alpha_h(t, xs[j]); sl[j] = alpha_hp(t, xs[j]); }
+  for (int j = 0; j < 3; ++j) {
+    hv[j] = alpha_h(t, xs[j]);
+    sl[j] = (xs[j] == m) ? hp_m : alpha_hp(t, xs[j]);   // the centre point is m unless the mode sits on a bound
+  }
   // --- segment boundaries: tangent intersections, clipped to [LO, HI] ---
   double z[4];
   z[0] = LO; z[3] = HI;
@@ -287,12 +313,20 @@ BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, dou
     if (zz > HI) zz = HI;
     z[j + 1] = zz;
   }
-  double hmax = hv[0];
-  if (hv[1] > hmax) hmax = hv[1];
-  if (hv[2] > hmax) hmax = hv[2];
+  // masses of the three envelope segments relative to the envelope's overall maximum (a
+  // piecewise-linear exponent peaks at a segment end): nothing overflows even when the
+  // tangent points do not bracket the mode
+  double top[3];
+  for (int j = 0; j < 3; ++j) {
+    const double el = hv[j] + sl[j] * (z[j] - xs[j]), er = hv[j] + sl[j] * (z[j + 1] - xs[j]);
+    top[j] = el > er ? el : er;
+  }
+  double hmax = top[0];
+  if (top[1] > hmax) hmax = top[1];
+  if (top[2] > hmax) hmax = top[2];
   double mass[3], tot = 0.0;
   for (int j = 0; j < 3; ++j) {
-    mass[j] = (z[j + 1] > z[j]) ? exp(hv[j] - hmax) * seg_mass(sl[j], z[j], z[j + 1], xs[j]) : 0.0;
+    mass[j] = (z[j + 1] > z[j]) ? exp(top[j] - hmax) * seg_unit(sl[j], z[j + 1] - z[j]) : 0.0;
     tot += mass[j];
   }
   double x = m;

@@ -114,45 +114,43 @@ def truncnorm0_draw(seed, it, purpose, cell, mean, sd, bits=32):
     return np.where(plain, x_plain, x_rob)
 
 
-def digamma(x):
+def digamma_trigamma(x):
+    """bnmf_rng.cuh::digamma_trigamma, operation for operation (shared reciprocals)."""
     x = np.asarray(x, dtype=np.float64).copy()
-    r = np.zeros_like(x)
+    r1 = np.zeros_like(x)
+    r2 = np.zeros_like(x)
     for _ in range(8):
         m = x < 6.0
         if not m.any():
             break
-        r = np.where(m, r - 1.0 / x, r)
+        inv = 1.0 / x
+        r1 = np.where(m, r1 - inv, r1)
+        r2 = np.where(m, r2 + inv * inv, r2)
         x = np.where(m, x + 1.0, x)
-    f = 1.0 / (x * x)
-    t = f * ((-1.0 / 12.0) + f * ((1.0 / 120.0) + f * ((-1.0 / 252.0) + f * ((1.0 / 240.0) + f * (-1.0 / 132.0)))))
-    return r + np.log(x) - 0.5 / x + t
+    inv = 1.0 / x
+    f = inv * inv
+    t1 = f * ((-1.0 / 12.0) + f * ((1.0 / 120.0) + f * ((-1.0 / 252.0) + f * ((1.0 / 240.0) + f * (-1.0 / 132.0)))))
+    psi = r1 + np.log(x) - 0.5 * inv + t1
+    t2 = inv + 0.5 * f + (f * inv) * ((1.0 / 6.0) + f * ((-1.0 / 30.0) + f * ((1.0 / 42.0) + f * (-1.0 / 30.0))))
+    return psi, r2 + t2
+
+
+def digamma(x):
+    return digamma_trigamma(x)[0]
 
 
 def trigamma(x):
-    x = np.asarray(x, dtype=np.float64).copy()
-    r = np.zeros_like(x)
-    for _ in range(8):
-        m = x < 6.0
-        if not m.any():
-            break
-        r = np.where(m, r + 1.0 / (x * x), r)
-        x = np.where(m, x + 1.0, x)
-    f = 1.0 / (x * x)
-    t = 1.0 / x + 0.5 * f + (f / x) * ((1.0 / 6.0) + f * ((-1.0 / 30.0) + f * ((1.0 / 42.0) + f * (-1.0 / 30.0))))
-    return r + t
+    return digamma_trigamma(x)[1]
 
 
-def _seg_mass(s, a, b, x0):
-    """integral of exp(s (x - x0)) over [a, b], anchored at the end with the larger
-    exponent so that expm1 only ever sees a non-positive argument (no overflow)."""
-    w = b - a
-    sw = s * w
-    small = np.abs(sw) < 1e-8
-    pos = sw > 0.0
-    base = np.exp(s * (np.where(pos, b, a) - x0))
+def _seg_unit(s, w):
+    """integral of exp(-|s| y) over [0, w]: the mass of a linear-exponent segment of width w
+    relative to its higher end (never overflows)."""
+    sw = np.abs(s) * w
+    small = sw < 1e-8
     with np.errstate(divide="ignore", invalid="ignore"):
-        big = base * np.expm1(-np.abs(sw)) / np.where(small, 1.0, np.where(pos, -s, s))
-    return np.where(small, np.exp(s * (a - x0)) * w * (1.0 + 0.5 * sw), big)
+        big = -np.expm1(-sw) / np.where(small, 1.0, np.abs(s))
+    return np.where(small, w * (1.0 - 0.5 * sw), big)
 
 
 def _seg_inv(s, a, b, q):
@@ -175,12 +173,20 @@ def alpha_logpdf(x, C, D, beta, X):
     return cm1 * np.log(x) - b * x - gammaln(x)
 
 
-def alpha_draw(seed, it, purpose, cell, C, D, beta, X):
+LAST_ALPHA_STATS = {}
+PSI_LO = -1000.5755719318103     # digamma(1e-3), literal shared with bnmf_rng.cuh
+PSI_HI = 9.21029037114285        # digamma(1e4)
+ALPHA_NEWTON = 16         # at most; stops at ALPHA_TOL relative (about 2 steps from the previous Alpha)
+ALPHA_TOL = 1e-2
+
+
+def alpha_draw(seed, it, purpose, cell, C, D, beta, X, x0=None):
     """armspp::arms(n_samples = 1, log_pdf, lower = 1e-3, upper = 1e4) for the shape
     parameter of the Gamma prior (R/sample_priors.R:356-397).  The target is
     log-concave (f'' = -(C-1)/x^2 - trigamma(x) < -C/x^2), so ARMS is exact ARS; drawn
     here exactly with a fixed three-tangent envelope (same construction as
-    bnmf_rng.cuh::alpha_draw)."""
+    bnmf_rng.cuh::alpha_draw).  x0 = start of the (approximate) mode search = the current
+    Alpha; the tangent points only affect the acceptance rate, not the distribution."""
     LO, HI = 1e-3, 1e4
     cell = np.asarray(cell, dtype=np.uint64)
     shp = cell.shape
@@ -194,22 +200,32 @@ def alpha_draw(seed, it, purpose, cell, C, D, beta, X):
     hp = lambda x: cm1 / x - b - digamma(x)  # noqa: E731
     hpp = lambda x: -cm1 / (x * x) - trigamma(x)  # noqa: E731
 
-    at_lo = hp(np.full(shp, LO)) <= 0.0
-    at_hi = (~at_lo) & (hp(np.full(shp, HI)) >= 0.0)
+    at_lo = cm1 / LO - b - PSI_LO <= 0.0
+    at_hi = (~at_lo) & (cm1 / HI - b - PSI_HI >= 0.0)
     a = np.full(shp, LO)
     bb = np.full(shp, HI)
-    x = np.where(C > 1.0, C, 1.0)
-    x = np.where(x >= HI, 0.5 * HI, x)
-    for _ in range(16):
+    xdef = np.where(C > 1.0, np.where(C < HI, C, 0.5 * HI), 1.0)
+    if x0 is None:
+        x = xdef
+    else:
+        x0 = np.broadcast_to(np.asarray(x0, dtype=np.float64), shp)
+        x = np.where((x0 > LO) & (x0 < HI), x0, xdef)
+    done = np.zeros(shp, dtype=bool)
+    steps = np.zeros(shp, dtype=np.int64)
+    for _ in range(ALPHA_NEWTON):
+        steps += ~done
         f = hp(x)
         a = np.where(f > 0.0, x, a)
         bb = np.where(f > 0.0, bb, x)
-        xn = x - f / hpp(x)
-        conv = np.abs(xn - x) <= 1e-10 * x
+        with np.errstate(over="ignore", invalid="ignore"):
+            xn = x * np.exp(-f / (x * hpp(x)))   # Newton step in log x
         bad = ~((xn > a) & (xn < bb))
-        xn = np.where(conv, x, np.where(bad, np.sqrt(a * bb), xn))
-        x = xn
+        xn = np.where(bad, np.sqrt(a * bb), xn)
+        conv = np.abs(xn - x) <= ALPHA_TOL * x
+        x = np.where(done, x, xn)            # the converging step is still taken
+        done = done | conv
     m = np.where(at_lo, LO, np.where(at_hi, HI, x))
+    hp_m = hp(m)
     s = 1.0 / np.sqrt(-hpp(m))
     x0 = np.where(m - s > 0.5 * m, m - s, 0.5 * m)
     x1 = m.copy()
@@ -229,7 +245,7 @@ def alpha_draw(seed, it, purpose, cell, C, D, beta, X):
     x2 = np.where(hi_case, HI, x2)
     xs = [x0, x1, x2]
     hv = [h(v) for v in xs]
-    sl = [hp(v) for v in xs]
+    sl = [np.where(v == m, hp_m, hp(v)) for v in xs]
     z = [np.full(shp, LO), None, None, np.full(shp, HI)]
     for j in range(2):
         den = sl[j] - sl[j + 1]
@@ -239,19 +255,25 @@ def alpha_draw(seed, it, purpose, cell, C, D, beta, X):
         zz = np.where(zz < LO, LO, zz)
         zz = np.where(zz > HI, HI, zz)
         z[j + 1] = zz
-    hmax = np.maximum(np.maximum(hv[0], hv[1]), hv[2])
+    # masses of the three envelope segments, each relative to the envelope's overall maximum
+    # (a piecewise-linear exponent peaks at a segment end), so nothing can overflow even when
+    # the tangent points do not bracket the mode
+    top = [np.maximum(hv[j] + sl[j] * (z[j] - xs[j]), hv[j] + sl[j] * (z[j + 1] - xs[j])) for j in range(3)]
+    hmax = np.maximum(np.maximum(top[0], top[1]), top[2])
     mass = []
     for j in range(3):
-        mj = np.where(z[j + 1] > z[j], np.exp(hv[j] - hmax) * _seg_mass(sl[j], z[j], z[j + 1], xs[j]), 0.0)
+        mj = np.where(z[j + 1] > z[j], np.exp(top[j] - hmax) * _seg_unit(sl[j], z[j + 1] - z[j]), 0.0)
         mass.append(mj)
     tot = (mass[0] + mass[1]) + mass[2]
     out = m.copy()
     todo = np.ones(shp, dtype=bool)
+    attempts = np.zeros(shp, dtype=np.int64)
     XS = np.stack(xs); HV = np.stack(hv); SL = np.stack(sl); Z = np.stack(z); MS = np.stack(mass)
     for t in range(MAX_ATTEMPTS):
         if not todo.any():
             break
         idx = np.nonzero(todo)
+        attempts[idx] += 1
         w = px.words(seed, it, purpose, cell[idx], t)
         r = px.u01(w[0]) * tot[idx]
         m0 = MS[0][idx]; m1 = MS[1][idx]
@@ -279,4 +301,5 @@ def alpha_draw(seed, it, purpose, cell, C, D, beta, X):
         sel = tuple(i[acc] for i in idx)
         out[sel] = xc[acc]
         todo[sel] = False
+    LAST_ALPHA_STATS.update(newton_steps=steps, attempts=attempts)   # diagnostics for tests / tuning
     return out

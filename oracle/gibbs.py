@@ -390,9 +390,9 @@ class OracleSampler:
         else:
             # sample_Beta_Pn (:323-329) then sample_Alpha_Pkn (:356-371) with the new Beta
             pp["Beta_p"] = dr.gamma_draw(s, it, px.PUR_HYP_P1, cp, hy["A_p"] + pp["Alpha_p"], hy["B_p"] + P)
-            pp["Alpha_p"] = dr.alpha_draw(s, it, px.PUR_HYP_P2, cp, hy["C_p"], hy["D_p"], pp["Beta_p"], P)
+            pp["Alpha_p"] = dr.alpha_draw(s, it, px.PUR_HYP_P2, cp, hy["C_p"], hy["D_p"], pp["Beta_p"], P, x0=pp["Alpha_p"])
             pp["Beta_e"] = dr.gamma_draw(s, it, px.PUR_HYP_E1, ce, hy["A_e"] + pp["Alpha_e"], hy["B_e"] + E)
-            pp["Alpha_e"] = dr.alpha_draw(s, it, px.PUR_HYP_E2, ce, hy["C_e"], hy["D_e"], pp["Beta_e"], E)
+            pp["Alpha_e"] = dr.alpha_draw(s, it, px.PUR_HYP_E2, ce, hy["C_e"], hy["D_e"], pp["Beta_e"], E, x0=pp["Alpha_e"])
 
     # -- P and E -------------------------------------------------------------------------
     def _prior_draw(self, side, n):

@@ -19,8 +19,8 @@ void hc_normal(uint64_t seed, uint32_t it, uint32_t pur, const uint64_t* cell, c
 void hc_exp(uint64_t seed, uint32_t it, uint32_t pur, const uint64_t* cell, const double* rate, double* out, long n) {
   for (long i = 0; i < n; ++i) out[i] = exponential_draw<double>(make_stream(seed, it, pur, cell[i]), rate[i]);
 }
-void hc_alpha(uint64_t seed, uint32_t it, uint32_t pur, const uint64_t* cell, const double* C, const double* D, const double* beta, const double* X, double* out, long n) {
-  for (long i = 0; i < n; ++i) out[i] = alpha_draw(make_stream(seed, it, pur, cell[i]), C[i], D[i], beta[i], X[i]);
+void hc_alpha(uint64_t seed, uint32_t it, uint32_t pur, const uint64_t* cell, const double* C, const double* D, const double* beta, const double* X, const double* x0, double* out, long n) {
+  for (long i = 0; i < n; ++i) out[i] = alpha_draw(make_stream(seed, it, pur, cell[i]), C[i], D[i], beta[i], X[i], x0[i]);
 }
 void hc_digamma(const double* x, double* d, double* t, long n) { for (long i = 0; i < n; ++i) { d[i] = digamma<double>(x[i]); t[i] = trigamma<double>(x[i]); } }
 }

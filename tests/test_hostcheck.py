@@ -67,8 +67,9 @@ def test_alpha(hc):
     D = np.exp(rng.uniform(-2, 3, N))
     beta = np.exp(rng.uniform(-4, 6, N))
     X = np.exp(rng.uniform(-12, 8, N))
-    got = _run(hc.hc_alpha, 77, 4, px.PUR_HYP_E2, C, D, beta, X)
-    want = dr.alpha_draw(77, 4, px.PUR_HYP_E2, CELLS, C, D, beta, X)
+    x0 = np.exp(rng.uniform(np.log(1e-4), np.log(1e5), N))     # incl. starts outside [1e-3, 1e4]
+    got = _run(hc.hc_alpha, 77, 4, px.PUR_HYP_E2, C, D, beta, X, x0)
+    want = dr.alpha_draw(77, 4, px.PUR_HYP_E2, CELLS, C, D, beta, X, x0=x0)
     # lgamma/digamma come from libm vs scipy: equal to rounding, and the accept test is discrete
     close = np.isclose(got, want, rtol=1e-8)
     assert close.mean() > 0.999, (~close).sum()

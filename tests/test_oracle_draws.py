@@ -40,10 +40,13 @@ def test_exponential_and_normal():
 
 @pytest.mark.parametrize("C,D,beta,X", [(64.5, 10.0, 3.0, 0.02), (22.0, 10.0, 9.0, 45.0), (1.5, 0.5, 1.0, 1.0),
                                         (0.5, 2.0, 0.2, 1e-4), (10.0, 10.0, 1e3, 1e3)])
-def test_alpha_conditional(C, D, beta, X):
+@pytest.mark.parametrize("start", ["default", "random"])
+def test_alpha_conditional(C, D, beta, X, start):
     """Exact draw from log f(x) = (C-1) log x - D x + x log(beta) + (x-1) log X - lgamma(x)
-    on [1e-3, 1e4] (R/sample_priors.R:357-365)."""
-    x = dr.alpha_draw(3, 9, px.PUR_HYP_P2, CELLS, C, D, beta, X)
+    on [1e-3, 1e4] (R/sample_priors.R:357-365), wherever the mode search starts (the tangent
+    points of the envelope only change the acceptance rate)."""
+    x0 = None if start == "default" else np.exp(np.random.default_rng(5).uniform(np.log(2e-3), np.log(5e3), CELLS.shape))
+    x = dr.alpha_draw(3, 9, px.PUR_HYP_P2, CELLS, C, D, beta, X, x0=x0)
     assert (x >= 1e-3).all() and (x <= 1e4).all()
     lo, hi = max(1e-3, x.min() * 0.2), min(1e4, x.max() * 3.0)
     grid = np.unique(np.concatenate([np.geomspace(1e-3, 1e4, 20001), np.linspace(lo, hi, 20001)]))
