@@ -301,6 +301,24 @@ struct Sampler : bnmf_handle {
     if (mh_setup()) return 1;
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
+    // default hyperprior parameters (get_default_*_hyperprior_params_, R/setup.R:123-181);
+    // bnmf_set_hyper overrides them.  mean(data) is over this handle's columns: sharded runs
+    // pass the global defaults explicitly.
+    {
+      long double sum = 0.0L;
+      for (long long i = 0; i < KG; ++i) sum += data[i];
+      const double mean = (double)(sum / (long double)KG), dN = (double)N;
+      struct DV { const char* n; double v; };
+      std::vector<DV> dv;
+      if (cfg.prior == BNMF_TRUNCNORMAL) dv = {{"M", 0.0}, {"S", std::sqrt(mean / dN)}, {"A", dN + 1.0}, {"B", std::sqrt(dN)}};
+      else if (cfg.prior == BNMF_EXPONENTIAL) dv = {{"A", 10.0 * std::sqrt(dN)}, {"B", 10.0 * std::sqrt(mean)}};
+      else dv = {{"A", 10.0 * std::sqrt(dN)}, {"B", 10.0}, {"C", 10.0 * std::sqrt(mean)}, {"D", 10.0}};
+      for (auto& e : dv)
+        for (const char* side : {"_p", "_e"}) {
+          const std::string nm = std::string(e.n) + side;
+          if (set_hyper(nm.c_str(), &e.v, 1, 1)) return 1;
+        }
+    }
     return 0;
   }
 

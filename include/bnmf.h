@@ -76,7 +76,9 @@ void bnmf_destroy(bnmf_handle* h);
 const char* bnmf_last_error(void);
 
 /* Hyperprior parameters, scalar (rows = cols = 1) or full matrix, as filled by
- * fill_hyperprior_params_ (R/setup.R:15-88).  Names: "A_p","B_p","C_p","D_p","M_p",
+ * fill_hyperprior_params_ (R/setup.R:15-88).  bnmf_create installs the reference's
+ * data-dependent defaults (R/setup.R:123-181, from mean(data) of the handle's columns and
+ * N); this call overrides them.  "alpha" / "beta" (scalars): sigmasq prior, default 3.  Names: "A_p","B_p","C_p","D_p","M_p",
  * "S_p" (K x N) and "A_e",...,"S_e" (N x G).  Matrices for *_e cover this shard. */
 int bnmf_set_hyper(bnmf_handle* h, const char* name, const double* v, int64_t rows, int64_t cols);
 

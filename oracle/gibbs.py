@@ -182,6 +182,40 @@ def dexp_log(x, rate):
     return np.log(rate) - rate * x
 
 
+# --------------------------------------------------------------------------------------
+# MAP over retained samples  (R/utils.R:194-288, R/helpers.R:35-79)
+# --------------------------------------------------------------------------------------
+def get_mode(A_list):
+    """get_mode (R/helpers.R:63-79): most frequent pattern; table() orders the pattern strings
+    alphabetically and the stable decreasing sort keeps that order among ties."""
+    keys = ["".join("1" if a else "0" for a in np.asarray(A).reshape(-1)) for A in A_list]
+    counts = {}
+    for k in keys:
+        counts[k] = counts.get(k, 0) + 1
+    mode = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))[0][0]
+    idx = [i for i, k in enumerate(keys) if k == mode]
+    return np.array([1.0 if c == "1" else 0.0 for c in mode]), idx
+
+
+def renormalize(P, E):
+    """renormalize (R/helpers.R:35-49): columns of P sum to 1, product P E unchanged."""
+    cs = P.sum(axis=0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return P / cs[None, :], E * cs[:, None]
+
+
+def get_MAP(P_list, E_list, A_list):
+    """get_MAP_ with final = FALSE (R/utils.R:194-261): samples oldest first; returns
+    (P_MAP, E_MAP, A_MAP, idx of the samples averaged)."""
+    A_map, idx = get_mode(A_list)
+    acc_P = acc_E = None
+    for i in idx:
+        P, E = renormalize(np.asarray(P_list[i], dtype=np.float64), np.asarray(E_list[i], dtype=np.float64))
+        acc_P = P if acc_P is None else acc_P + P
+        acc_E = E if acc_E is None else acc_E + E
+    return acc_P / len(idx), acc_E / len(idx), A_map, idx
+
+
 class OracleSampler:
     """State + one-iteration update of bayesNMF_sampler (R/bayesNMF_sampler.R:8-747),
     restricted to what the hot path touches."""

@@ -1,0 +1,50 @@
+"""Sample ring (record_sample, R/bayesNMF_sampler.R:651-672) and get_MAP_ on the device
+(R/utils.R:194-288) against the oracle's restatement, through the C ABI."""
+import numpy as np
+import pytest
+
+from tests.util import synth_counts
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("lik,prior,MH,learn", [("poisson", "truncnormal", True, True), ("poisson", "gamma", False, False),
+                                                ("normal", "exponential", False, True)])
+def test_ring_and_map(built_lib, lik, prior, MH, learn):
+    from bayesnmf_b200 import BnmfError, Handle
+    from oracle.gibbs import get_MAP, get_temp_sched
+    K, G, N, cap = 96, 40, 5, 24
+    M, _, _ = synth_counts(K, G, 3, 1500.0, seed=2)
+    h = Handle(M, N, likelihood=lik, prior=prior, MH=MH, learning_rank=learn, seed=4, ring_cap=cap)
+    h.set_temperature_schedule(get_temp_sched(80, 30))     # hyperparameters: the library's defaults (R/setup.R:123-181)
+    h.init_from_prior()
+    Ps, Es, As = [h.get_state("P")], [h.get_state("E")], [h.get_state("A")]
+    for _ in range(37):
+        h.step(1)
+        Ps.append(h.get_state("P")); Es.append(h.get_state("E")); As.append(h.get_state("A"))
+    assert h.ring_count() == cap
+    for ago in (0, 1, 7, cap - 1):       # update_list keeps the newest MAP_over samples (R/helpers.R:111-119)
+        np.testing.assert_array_equal(h.get_sample("P", ago), Ps[-1 - ago])
+        np.testing.assert_array_equal(h.get_sample("E", ago), Es[-1 - ago])
+        np.testing.assert_array_equal(h.get_sample("A", ago), As[-1 - ago])
+    with pytest.raises(BnmfError):
+        h.get_sample("P", cap)
+    for n_s in (cap, 10, 1):
+        P_map, E_map, A_map, n_match = h.get_map(n_s)
+        oP, oE, oA, idx = get_MAP(Ps[-n_s:], Es[-n_s:], As[-n_s:])
+        assert n_match == len(idx)
+        np.testing.assert_array_equal(A_map, oA)
+        np.testing.assert_allclose(P_map, oP, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(E_map, oE, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(P_map.sum(axis=0), 1.0, rtol=1e-12)     # renormalised signatures
+    with pytest.raises(BnmfError):
+        h.get_map(cap + 1)
+
+
+def test_map_without_ring_fails(built_lib):
+    from bayesnmf_b200 import BnmfError, Handle
+    M, _, _ = synth_counts(96, 10, 3, 500.0, seed=0)
+    h = Handle(M, 3, likelihood="poisson", prior="gamma", MH=False, seed=1)
+    h.init_from_prior()
+    with pytest.raises(BnmfError):
+        h.get_map(1)

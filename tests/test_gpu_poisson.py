@@ -99,3 +99,18 @@ def test_step_chunks_equal_single_steps(built_lib):
     np.testing.assert_array_equal(ra["metrics"], np.concatenate([r["metrics"] for r in rows]))
     np.testing.assert_array_equal(ra["P"], np.concatenate([r["P"] for r in rows]))
     np.testing.assert_array_equal(a.get_state("E"), b.get_state("E"))
+
+
+@pytest.mark.parametrize("lik,prior,MH", [("poisson", "gamma", False), ("poisson", "truncnormal", True), ("normal", "exponential", False)])
+def test_default_hyperparameters(built_lib, lik, prior, MH):
+    """Without bnmf_set_hyper the library uses the reference's data-dependent defaults
+    (get_default_*_hyperprior_params_, R/setup.R:123-181), like the oracle."""
+    from bayesnmf_b200 import Handle
+    from oracle.gibbs import OracleSampler
+    M, _, _ = synth_counts(96, 30, 4, 800.0, seed=6)
+    o = OracleSampler(M, 4, lik, prior, MH=MH, seed=2)
+    h = Handle(M, 4, likelihood=lik, prior=prior, MH=MH, seed=2)
+    h.init_from_prior()
+    o.step(); h.step(1)
+    np.testing.assert_allclose(h.get_state("P"), o.params["P"], rtol=1e-6, atol=1e-300)
+    np.testing.assert_allclose(h.get_state("E"), o.params["E"], rtol=1e-6, atol=1e-300)

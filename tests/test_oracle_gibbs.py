@@ -156,3 +156,23 @@ def test_reference_example_known_answer():
     best = c.max(axis=0)
     assert sorted(c.argmax(axis=0)) == [0, 1, 2, 3]
     assert (best[[0, 2, 3]] > 0.995).all() and best[1] > 0.93     # SBS40 is the flat, hard one
+
+
+def test_get_mode_and_MAP():
+    """get_mode ties go to the alphabetically first pattern (table() order + stable sort,
+    R/helpers.R:63-79); get_MAP averages the renormalised matching samples (R/utils.R:236-250)."""
+    rng = np.random.default_rng(0)
+    A = [np.array([1, 0, 1]), np.array([1, 1, 1]), np.array([1, 1, 1]), np.array([1, 0, 1])]
+    mode, idx = og.get_mode(A)
+    assert list(mode) == [1, 0, 1] and idx == [0, 3]
+    P = [rng.gamma(1.0, 1.0, (6, 3)) for _ in A]
+    E = [rng.gamma(1.0, 5.0, (3, 4)) for _ in A]
+    Pm, Em, Am, idx = og.get_MAP(P, E, A)
+    want_P = (P[0] / P[0].sum(0) + P[3] / P[3].sum(0)) / 2
+    want_E = (E[0] * P[0].sum(0)[:, None] + E[3] * P[3].sum(0)[:, None]) / 2
+    np.testing.assert_allclose(Pm, want_P, rtol=1e-14)
+    np.testing.assert_allclose(Em, want_E, rtol=1e-14)
+    np.testing.assert_allclose(Pm.sum(0), 1.0)
+    for p, e in zip(P, E):                      # renormalize keeps the product
+        rp, re = og.renormalize(p, e)
+        np.testing.assert_allclose(rp @ re, p @ e, rtol=1e-12)
