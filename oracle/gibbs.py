@@ -223,7 +223,7 @@ class OracleSampler:
     def __init__(self, data, N, likelihood="poisson", prior="truncnormal", MH=None,
                  learning_rank=False, rank_method="SBFI", seed=0,
                  hyperprior_params=None, init_prior_params=None, init_params=None,
-                 temperature_schedule=None, g0=0, G_total=None, mean_data=None, bits=32):
+                 temperature_schedule=None, g0=0, G_total=None, mean_data=None, bits=32, reduce_fn=None):
         self.data = np.asarray(data, dtype=np.float64)
         self.K, self.G = self.data.shape
         self.N = int(N)
@@ -234,6 +234,9 @@ class OracleSampler:
         self.seed, self.bits = int(seed), bits
         self.g0 = int(g0)
         self.G_total = int(G_total) if G_total is not None else self.G
+        # genome-sharded runs (Poisson latent-count models): `reduce_fn(array) -> array` sums an
+        # array over the shards, at exactly the points where the CUDA path calls NCCL
+        self.reduce = reduce_fn if reduce_fn is not None else (lambda a: a)
         self.iter = 1                      # state$iter  (R/bayesNMF_sampler.R:39-43)
         self.converged = False
         self.temperature_schedule = (np.ones(100000) if temperature_schedule is None
@@ -361,29 +364,37 @@ class OracleSampler:
     def get_loglik(self, **kw):
         return float(self.loglik_matrix(**kw).sum())
 
-    def log_prior(self):
-        """log prior part of get_logpost_  (R/utils.R:131-175); all N signatures count."""
+    def log_prior_parts(self):
+        """log prior part of get_logpost_  (R/utils.R:131-175), P side and E side; all N
+        signatures count."""
         P, E, pp = self.params["P"], self.params["E"], self.prior_params
         if self.prior == "truncnormal":
-            return float(dtruncnorm0_log(P, pp["Mu_p"], np.sqrt(pp["Sigmasq_p"])).sum()
-                         + dtruncnorm0_log(E, pp["Mu_e"], np.sqrt(pp["Sigmasq_e"])).sum())
+            return (float(dtruncnorm0_log(P, pp["Mu_p"], np.sqrt(pp["Sigmasq_p"])).sum()),
+                    float(dtruncnorm0_log(E, pp["Mu_e"], np.sqrt(pp["Sigmasq_e"])).sum()))
         if self.prior == "exponential":
-            return float(dexp_log(P, pp["Lambda_p"]).sum() + dexp_log(E, pp["Lambda_e"]).sum())
-        return float(dgamma_log(P, pp["Alpha_p"], pp["Beta_p"]).sum()
-                     + dgamma_log(E, pp["Alpha_e"], pp["Beta_e"]).sum())
+            return float(dexp_log(P, pp["Lambda_p"]).sum()), float(dexp_log(E, pp["Lambda_e"]).sum())
+        return (float(dgamma_log(P, pp["Alpha_p"], pp["Beta_p"]).sum()),
+                float(dgamma_log(E, pp["Alpha_e"], pp["Beta_e"]).sum()))
+
+    def log_prior(self):
+        a, b = self.log_prior_parts()
+        return a + b
 
     def compute_metrics_(self):
         """compute_metrics_ + update_sample_metrics_  (R/utils.R:412-455, :339-348)."""
         A = self.params["A"]
         Mhat = self.get_Mhat()
         n_params = A.sum() * (self.G_total + self.K)
-        loglik = self.get_loglik()
-        logpost = loglik + self.log_prior()
         Mh = np.maximum(Mhat, 1e-6)
         Mp = np.maximum(self.data, 1e-6)
+        lp_P, lp_E = self.log_prior_parts()
+        # sums over this shard's genomes, then over shards (identity when not sharded)
+        part = self.reduce(np.array([self.get_loglik(), np.sum((Mhat - self.data) ** 2), np.sum(Mp * np.log(Mp / Mh)), lp_E]))
+        loglik = float(part[0])
+        logpost = loglik + lp_P + float(part[3])
         m = dict(iter=self.iter,
-                 RMSE=float(np.sqrt(np.mean((Mhat - self.data) ** 2))),
-                 KL=float(np.sum(Mp * np.log(Mp / Mh))),        # padded_KL_, R/utils.R:467-471
+                 RMSE=float(np.sqrt(part[1] / (self.K * self.G_total))),
+                 KL=float(part[2]),        # padded_KL_, R/utils.R:467-471
                  loglikelihood=loglik, logposterior=logpost, n_params=float(n_params),
                  BIC=float(-2.0 * loglik + n_params * np.log(self.G_total)),
                  rank=float(A.sum()), temp=float(self.temperature_schedule[self.iter - 1]))
@@ -629,8 +640,7 @@ class OracleSampler:
         T = self.temperature_schedule[self.iter - 1]
         A0 = self.params["A"].copy(); A0[n] = 0
         A1 = self.params["A"].copy(); A1[n] = 1
-        l0 = self.get_loglik(A=A0)
-        l1 = self.get_loglik(A=A1)
+        l0, l1 = (float(v) for v in self.reduce(np.array([self.get_loglik(A=A0), self.get_loglik(A=A1)])))
         if self.rank_method == "SBFI":
             b0 = l0 - A0.sum() * (G + K) * np.log(G) / 2.0
             b1 = l1 - A1.sum() * (G + K) * np.log(G) / 2.0
@@ -670,7 +680,7 @@ class OracleSampler:
     @property
     def rowsumE(self):
         """rowSums(E) as the kernels accumulate it: fixed point 2^-24, exact integer sum."""
-        return np.rint(self.params["E"] * 16777216.0).sum(axis=1) / 16777216.0
+        return self.reduce(np.rint(self.params["E"] * 16777216.0).sum(axis=1)) / 16777216.0
 
     def sample_params_(self, skip=(), from_prior=False):
         """sample_params_  (R/sample_params.R:51-89): P (n = 1..N) -> E (n = 1..N) -> R, A
@@ -692,6 +702,7 @@ class OracleSampler:
         if self.likelihood == "poisson" and not self.MH and "Z" not in skip:
             self.SP, self.SE = sample_Z_stats(self.data, p["P"], p["A"], p["E"], self.seed, self.iter,
                                               g0=self.g0, bits=self.bits)
+            self.SP = self.reduce(self.SP)
         if self.likelihood == "normal" and "sigmasq" not in skip:
             p["sigmasq"] = self.sample_sigmasq()
 
