@@ -42,6 +42,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, workload, prec, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json names the capture); None
+    when no capture of this exact configuration exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(f"{kernel}:{workload}:{prec}")
+    return None if e is None else e["bytes_per_launch"]
+
+
 def z_algorithmic_bytes(K, G, N, elem):
     """Bytes the fused latent-count kernel must move per launch: M read once (int32),
     E read once and SE written once, P read and SP written once."""
@@ -94,17 +105,11 @@ def synth(w, seed=0):
     return M
 
 
-def set_default_hypers(h, w, mean_data):
-    from bayesnmf_b200.hyperpriors import fill_hyperprior_params
-    for k, v in fill_hyperprior_params(None, w["prior"], mean_data, w["N"]).items():
-        h.set_hyper(k, v)
-
-
 # ------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from bayesnmf_b200 import Handle, comm_unique_id
+    from bayesnmf_b200.shard import shard_bounds, sharded_handle
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -118,22 +123,21 @@ def run_b200(args):
     w = dict(WORKLOADS[args.workload])
     K, G, N = w["K"], w["G"], w["N"]
     M = synth(w)
-    mean_data = float(M.mean())
-    g_lo, g_hi = (G * rank) // world, (G * (rank + 1)) // world
+    g_lo, g_hi = shard_bounds(G, rank, world)
     prec = args.precision
     elem = 8 if prec == "f64" else 4
 
+    class _Solo:                      # the plumbing interface of torch.distributed for a 1-rank run
+        @staticmethod
+        def get_rank(): return 0
+        @staticmethod
+        def get_world_size(): return 1
+        @staticmethod
+        def is_initialized(): return False
+
     def make(ring_cap=0):
-        h = Handle(M[:, g_lo:g_hi], N, likelihood=w["likelihood"], prior=w["prior"], MH=w["MH"], seed=1,
-                   precision=prec, device=local, ring_cap=ring_cap, g0=g_lo, G_total=G)
-        set_default_hypers(h, w, mean_data)
-        if world > 1:
-            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
-            dist.broadcast(uid, 0)
-            h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
-        return h
+        return sharded_handle(M, N, dist if world > 1 else _Solo, device=local, likelihood=w["likelihood"], prior=w["prior"],
+                              MH=w["MH"], seed=1, precision=prec, ring_cap=ring_cap)
 
     def sync():
         torch.cuda.synchronize()
@@ -219,7 +223,7 @@ def run_b200(args):
         "e2e": {"value": args.steps / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "handle creation + upload of M + prior draw + steps with all metric rows and P/A samples to host + final E; wall clock"},
         "roofline": {"kernel": "k_zstat", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_zstat", args.workload, prec, world), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": zb, "avg_launch_ms": z_avg_ms,
                      "share_of_step": z_ms / iter_ms if iter_ms else None,
                      "latent_picks_per_s": float(M[:, g_lo:g_hi].sum()) / (z_avg_ms * 1e-3) if z_avg_ms > 0 else None},

@@ -19,8 +19,16 @@ for i, h in enumerate(hdr):
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
+body = []
+for r in rows[2:]:
+    if len(r) < len(hdr):
+        if body: break          # next kernel of the report
+        continue
+    if r[ix['Source']] == 'Source':
+        break
+    body.append(r)
 data = [(r[ix['Source']].strip(), float(r[ix['Instructions Executed']] or 0), float(r[ix['# Samples']] or 0),
-         float(r[ix['Avg. Threads Executed']] or 0)) for r in rows[2:] if len(r) >= len(hdr)]
+         float(r[ix['Avg. Threads Executed']] or 0)) for r in body]
 T = sum(x[1] for x in data); S = sum(x[2] for x in data)
 print("# SASS regions (instructions executed %, stall samples %, avg active threads)")
 for i in range(0, len(data), chunk):
