@@ -68,6 +68,7 @@ def lib():
     L.bnmf_get_map.argtypes = [vp, i32, dp, dp, dp, ctypes.POINTER(i32)]
     L.bnmf_comm_unique_id.argtypes = [ctypes.c_char_p]
     L.bnmf_comm_init.argtypes = [vp, ctypes.c_char_p, i32, i32]
+    L.bnmf_comm_share.argtypes = [vp, vp]
     L.bnmf_timing.argtypes = [vp, dp, dp, dp, ctypes.POINTER(i64)]
     L.bnmf_set_l2_flush.argtypes = [vp, ctypes.c_size_t]
     L.bnmf_sample_z.argtypes = [vp, i32, dp]
@@ -78,7 +79,7 @@ def lib():
 EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
            "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
            "bnmf_step", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_comm_unique_id",
-           "bnmf_comm_init", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z"]
+           "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z"]
 
 
 def _dp(a):
@@ -199,6 +200,9 @@ class Handle:
 
     def comm_init(self, uid, rank, world):
         self._ck(lib().bnmf_comm_init(self._h, uid, int(rank), int(world)))
+
+    def comm_share(self, other):
+        self._ck(lib().bnmf_comm_share(self._h, other._h))
 
     def timing(self):
         t = ctypes.c_double(); i = ctypes.c_double(); z = ctypes.c_double(); l = ctypes.c_int64()

@@ -4,9 +4,11 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <cmath>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -58,6 +60,11 @@ static int load_nccl() {
 #undef LD
   return 0;
 }
+// a communicator shared by the handles of one process (chains / ranks of a BIC fan-out reuse it)
+struct CommBox {
+  void* comm = nullptr;
+  ~CommBox() { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
+};
 enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_INT32 = 2 };
 
 // ---------------------------------------------------------------------------------
@@ -73,6 +80,8 @@ struct bnmf_handle {
   virtual int get_sample(const char* name, int ago, double* out, int64_t len) = 0;
   virtual int get_map(int n_samples, double* P, double* E, double* A, int* n_match) = 0;
   virtual int comm_init(const char* id, int rank, int world) = 0;
+  virtual int comm_share(bnmf_handle* src) = 0;
+  std::shared_ptr<CommBox> commbox; int world = 1, rank = 0;
   virtual int timing(double* total, double* iter, double* z, int64_t* launches) = 0;
   virtual int set_l2_flush(size_t bytes) = 0;
   virtual int sample_z(int iter, double* ms) = 0;
@@ -122,6 +131,15 @@ template <typename T> static __global__ void k_data_consts_real(const T* Mr, lon
   if (threadIdx.x == 0) { out[2 * blockIdx.x] = 0.0; out[2 * blockIdx.x + 1] = b; }
 }
 
+// samples$P / samples$A of the iteration into row ctrl->row of the step's history buffers
+template <typename T> static __global__ void k_hist_copy(Dev<T> d, T* P_hist, int32_t* A_hist) {
+  const long long KN = (long long)d.K * d.N;
+  const long long row = d.ctrl->row;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (P_hist && i < KN) P_hist[row * KN + i] = d.P[i];
+  if (A_hist && i < d.N) A_hist[row * d.N + i] = d.A[i];
+}
+
 enum StType { ST_T, ST_I32, ST_U64 };
 struct StEntry { void* p; long long len; StType ty; };
 
@@ -141,7 +159,7 @@ struct Sampler : bnmf_handle {
   T* P_hist = nullptr; int32_t* A_hist = nullptr;
   double* h_metrics = nullptr;                            // pinned
   int NP = 0; size_t z_smem = 0;
-  void* comm = nullptr; int world = 1, rank = 0;
+  void* comm = nullptr;
   long long* red_i64 = nullptr;                           // [K*N + N] packed int64 reduction buffer
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> zev, iev;
@@ -153,12 +171,13 @@ struct Sampler : bnmf_handle {
 
   ~Sampler() override {
     cudaSetDevice(cfg.device);
-    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    commbox.reset();
     for (void* p : allocs) cudaFree(p);
     if (h_metrics) cudaFreeHost(h_metrics);
     for (auto e : zev) cudaEventDestroy(e);
     for (auto e : iev) cudaEventDestroy(e);
     if (flush_buf) cudaFree(flush_buf);
+    if (gexec) cudaGraphExecDestroy(gexec);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -382,6 +401,7 @@ struct Sampler : bnmf_handle {
     k_cvt_in<T><<<blocks(n, 256), 256, 0, stream>>>(stage, p, n);
     CK(cudaStreamSynchronize(stream));
     it->second->p = p; it->second->is_matrix = n != 1;
+    drop_graph();      // the captured kernels hold the old pointer
     return 0;
   }
   int set_state(const char* name, const double* v, int64_t len) override {
@@ -431,6 +451,7 @@ struct Sampler : bnmf_handle {
     CK(cudaMemcpyAsync(p, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
     d.temps = p; d.n_temps = (int)n; have_temps = true;
+    drop_graph();
     return 0;
   }
 
@@ -445,9 +466,17 @@ struct Sampler : bnmf_handle {
       return fail("bnmf_comm_init: genome sharding is built for the Poisson latent-count models; run Normal / MH models as independent chains, one per GPU");
     if (load_nccl()) return 1;
     Id128 uid; memcpy(uid.b, id, 128);
-    int r = g_nccl.CommInitRank(&comm, world_, uid, rank_);
+    auto box = std::make_shared<CommBox>();
+    int r = g_nccl.CommInitRank(&box->comm, world_, uid, rank_);
     if (r) return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
-    world = world_; rank = rank_;
+    commbox = box; comm = box->comm; world = world_; rank = rank_;
+    return 0;
+  }
+  int comm_share(bnmf_handle* src) override {
+    if (sweep_model)
+      return fail("bnmf_comm_share: genome sharding is built for the Poisson latent-count models");
+    if (!src->commbox) return fail("bnmf_comm_share: the source handle has no communicator");
+    commbox = src->commbox; comm = commbox->comm; world = src->world; rank = src->rank;
     return 0;
   }
   int allreduce_stats() {   // SP + rowsumE_fx (exact int64 sums)
@@ -550,6 +579,48 @@ struct Sampler : bnmf_handle {
   }
   int init_sigmasq_prior();
 
+  // ---- one iteration as a CUDA graph -------------------------------------------------
+  // Small and sweep-based problems are launch-bound (60-170 tiny kernels per iteration at
+  // 96 x 500): the fixed launch sequence of an iteration is captured once per
+  // (converged, want P, want A) and replayed.  Everything that changes from one iteration to
+  // the next (iteration number, metrics row, ring slot) lives in device memory (Ctrl).
+  cudaGraphExec_t gexec = nullptr; int gkey = -1; int glaunches = 0;
+  void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } gkey = -1; }
+  bool graphs_allowed() const {
+    static const bool off = getenv("BNMF_GRAPH") && !strcmp(getenv("BNMF_GRAPH"), "0");
+    if (off || world > 1) return false;
+    return sweep_model || (long long)cfg.K * cfg.G <= 2000000LL;
+  }
+  int launch_iteration(bool wantP, bool wantA, cudaEvent_t z0, cudaEvent_t z1) {
+    const long long KN = (long long)cfg.K * cfg.N;
+    k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); ++launches;
+    if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (poisson_iteration(0, 0, z0, z1)) return 1; }
+    else { if (mh_iteration(0, 0)) return 1; }
+    if (finish_iteration()) return 1;
+    if (wantP || wantA) {
+      k_hist_copy<T><<<blocks(KN, 256), 256, 0, stream>>>(d, wantP ? P_hist : nullptr, wantA ? A_hist : nullptr); ++launches;
+    }
+    return 0;
+  }
+  int ensure_graph(bool wantP, bool wantA) {
+    const int key = (h_converged ? 1 : 0) | (wantP ? 2 : 0) | (wantA ? 4 : 0);
+    if (gexec && gkey == key) return 0;
+    if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+    cudaGraph_t g = nullptr;
+    const int before = launches;
+    CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = launch_iteration(wantP, wantA, nullptr, nullptr);
+    const cudaError_t e = cudaStreamEndCapture(stream, &g);
+    glaunches = launches - before; launches = before;
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (e != cudaSuccess) return fail("graph capture of the iteration failed: %s", cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { gexec = nullptr; return fail("cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
+    gkey = key;
+    return 0;
+  }
+
   int step(int n_iters, int converged, double* metrics, double* P_out, double* A_out) override {
     CK(cudaSetDevice(cfg.device));
     if (n_iters < 0) return fail("bnmf_step: n_iters < 0");
@@ -557,30 +628,24 @@ struct Sampler : bnmf_handle {
     const int K = cfg.K, N = cfg.N; const long long KN = (long long)K * N;
     launches = 0;
     last_z_ms = 0; last_iter_ms = 0;
+    const bool use_graph = graphs_allowed();
+    if (use_graph) { if (ensure_graph(P_out != nullptr, A_out != nullptr)) return 1; }
     CK(cudaEventRecord(ev0, stream));
     int done = 0;
-    std::vector<double> tmp;
     while (done < n_iters) {
       const int chunk = std::min(n_iters - done, d.metrics_cap);
       // ctrl.converged / ctrl.row for this chunk (iter and ring position live on the device)
       int two[2] = {converged, -1};
       CK(cudaMemcpyAsync(&d.ctrl->converged, two, sizeof(two), cudaMemcpyHostToDevice, stream));
-      const bool timez = time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
+      const bool timez = !use_graph && time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
       if (timez) while ((int)zev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); zev.push_back(e); }
       while ((int)iev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); iev.push_back(e); }
       for (int i = 0; i < chunk; ++i) {
         if (flush_bytes) CK(cudaMemsetAsync(flush_buf, i & 0xff, flush_bytes, stream));
         CK(cudaEventRecord(iev[2 * i], stream));
-        k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); ++launches;
-        if (cfg.likelihood == BNMF_POISSON && !cfg.MH) {
-          if (poisson_iteration(0, 0, timez ? zev[2 * i] : nullptr, timez ? zev[2 * i + 1] : nullptr)) return 1;
-        } else {
-          if (mh_iteration(0, 0)) return 1;
-        }
-        if (finish_iteration()) return 1;
+        if (use_graph) { CK(cudaGraphLaunch(gexec, stream)); launches += glaunches; }
+        else if (launch_iteration(P_out != nullptr, A_out != nullptr, timez ? zev[2 * i] : nullptr, timez ? zev[2 * i + 1] : nullptr)) return 1;
         CK(cudaEventRecord(iev[2 * i + 1], stream));
-        if (P_out) CK(cudaMemcpyAsync(P_hist + (long long)i * KN, d.P, sizeof(T) * KN, cudaMemcpyDeviceToDevice, stream));
-        if (A_out) CK(cudaMemcpyAsync(A_hist + (long long)i * N, d.A, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, stream));
       }
       CK(cudaMemcpyAsync(h_metrics, d.metrics, sizeof(double) * MC_COLS * chunk, cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
@@ -753,6 +818,7 @@ int bnmf_comm_unique_id(char* id128) {
   return 0;
 }
 int bnmf_comm_init(bnmf_handle* h, const char* id, int32_t rank, int32_t world) { NEED(h); return h->comm_init(id, rank, world); }
+int bnmf_comm_share(bnmf_handle* h, bnmf_handle* src) { NEED(h); NEED(src); return h->comm_share(src); }
 int bnmf_timing(bnmf_handle* h, double* t, double* it, double* z, int64_t* l) { NEED(h); return h->timing(t, it, z, l); }
 int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes) { NEED(h); return h->set_l2_flush(bytes); }
 int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* ms) { NEED(h); return h->sample_z(iter, ms); }

@@ -40,9 +40,10 @@ def broadcast_bytes(payload, nbytes, dist, src=0):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def sharded_handle(M, N, dist, device=0, hyperprior_params=None, **kw):
+def sharded_handle(M, N, dist, device=0, hyperprior_params=None, share_comm=None, **kw):
     """Handle for this rank's block of the full matrix M (K x G_total), joined to the NCCL
-    communicator of all ranks, with the hyperprior defaults of the *whole* data set."""
+    communicator of all ranks (a new one, or the one `share_comm` -- another handle of this
+    process -- already holds), with the hyperprior defaults of the *whole* data set."""
     from . import Handle, comm_unique_id
     from .hyperpriors import fill_hyperprior_params
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -54,7 +55,9 @@ def sharded_handle(M, N, dist, device=0, hyperprior_params=None, **kw):
         if np.ndim(value) == 2 and name.endswith("_e"):
             value = np.asarray(value)[:, lo:hi]
         h.set_hyper(name, value)
-    if world > 1:
+    if world > 1 and share_comm is not None:
+        h.comm_share(share_comm)
+    elif world > 1:
         uid = broadcast_bytes(comm_unique_id() if rank == 0 else b"", 128, dist)
         h.comm_init(uid, rank, world)
     return h

@@ -129,6 +129,9 @@ int bnmf_get_map(bnmf_handle* h, int32_t n_samples, double* P_map, double* E_map
  * bnmf_step sums SP, rowSums(E) and the metric partials over ranks with NCCL. */
 int bnmf_comm_unique_id(char* id128);
 int bnmf_comm_init(bnmf_handle* h, const char* id128, int32_t rank, int32_t world);
+/* Let `h` use the communicator `src` (same process, same device) already joined: further
+ * chains or the fixed-rank samplers of a BIC fan-out need no second rendezvous. */
+int bnmf_comm_share(bnmf_handle* h, bnmf_handle* src);
 
 /* Device timing of the last bnmf_step call (CUDA events on the handle's stream), in
  * milliseconds: total = the whole call; iter = sum over iterations of the span from
