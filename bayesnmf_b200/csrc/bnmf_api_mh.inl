@@ -91,7 +91,7 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
     launches += 3;
     const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
     const size_t psm = (size_t)p_kx * p_gy * 2 * sizeof(double);
-    const int dblocks = (K + 127) / 128;
+    const int dblocks = (K + 3) / 4;       // k_p_draw / k_p_accept: a warp per mutation type
     for (int n = 0; n < N; ++n) {
       k_p_pass1<T><<<pgrid, pblock, psm, stream>>>(d, n, n ? n - 1 : -1);
       k_p_draw<T><<<dblocks, 128, 0, stream>>>(d, n);

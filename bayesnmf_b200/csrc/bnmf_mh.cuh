@@ -47,11 +47,14 @@ template <typename T> __device__ __forceinline__ double Mat(const Dev<T>& d, lon
 // the lgamma(M + 1) and -log sqrt(2 pi) terms cancel inside the cell.
 __device__ __forceinline__ double mh_cell(double m, double mh_old, double mh_new) {
   const double lo = mh_old > 1e-6 ? mh_old : 1e-6, ln = mh_new > 1e-6 ? mh_new : 1e-6;
-  const double dp = (m * log(ln) - ln) - (m * log(lo) - lo);
+  const double Lo = log(lo), Ln = log(ln);
+  const double dp = (m * Ln - ln) - (m * Lo - lo);
   const double vo = mh_new > 1.0 ? mh_new : 1.0, vn = mh_old > 1.0 ? mh_old : 1.0;
+  // log(max(x, 1)) = max(log(max(x, 1e-6)), 0): two logarithms serve all four densities
+  const double Lvo = Ln > 0.0 ? Ln : 0.0, Lvn = Lo > 0.0 ? Lo : 0.0;
   const double ro = m - mh_old, rn = m - mh_new;
-  const double n_old = -0.5 * log(vo) - 0.5 * (ro * ro) / vo;
-  const double n_new = -0.5 * log(vn) - 0.5 * (rn * rn) / vn;
+  const double n_old = -0.5 * Lvo - 0.5 * (ro * ro) / vo;
+  const double n_new = -0.5 * Lvn - 0.5 * (rn * rn) / vn;
   return dp + (n_old - n_new);
 }
 __device__ __forceinline__ double mh_ratio(double D) {
@@ -186,19 +189,27 @@ __global__ void k_p_pass1(Dev<T> d, int n, int n_prev) {
   if (k < K) {
     const double dv = n_prev >= 0 ? d.dvec[k] : 0.0;
     const double pkn = (double)d.P[k + (long long)K * n];
+    // restrict-qualified views: lets the loads of several genomes be in flight at once
+    T* __restrict__ Mh = d.Mhat;
+    const T* __restrict__ Ev = d.E;
+    const T* __restrict__ Sg = d.sigmasq;
+    const int32_t* __restrict__ Mi = d.Mi;
+    const T* __restrict__ Mr = d.Mr;
+#pragma unroll 4
     for (long long g = gbeg + gy; g < gend; g += GY) {
       const long long i = k + (long long)K * g;
-      double mh = (double)d.Mhat[i];
+      double mh = (double)Mh[i];
       if (n_prev >= 0) {
-        mh = (double)(T)(mh + dv * (double)d.E[n_prev + (long long)N * g]);
-        d.Mhat[i] = (T)mh;
+        mh = (double)(T)(mh + dv * (double)Ev[n_prev + (long long)N * g]);
+        Mh[i] = (T)mh;
       }
       if (An) {
-        const double e = (double)d.E[n + (long long)N * g];
-        const double s = normal ? (double)d.sigmasq[g] : mh;
+        const double e = (double)Ev[n + (long long)N * g];
+        const double inv = 1.0 / (normal ? (double)Sg[g] : mh);
         const double mh_no = mh - pkn * e;
-        num1 += e * ((Mat(d, i) - mh_no) / s);
-        den += (e * e) * (1.0 / s);
+        const double m = normal ? (double)Mr[i] : (double)Mi[i];
+        num1 += e * ((m - mh_no) * inv);
+        den += (e * e) * inv;
       }
     }
   }
@@ -223,10 +234,15 @@ __global__ void k_p_pass2(Dev<T> d, int n) {
   double D = 0.0;
   if (k < K && d.A[n]) {
     const double dp = d.prop[k] - (double)d.P[k + (long long)K * n];
+    const T* __restrict__ Mh = d.Mhat;
+    const T* __restrict__ Ev = d.E;
+    const bool normal = d.likelihood == LIK_NORMAL;
+#pragma unroll 4
     for (long long g = gbeg + gy; g < gend; g += GY) {
       const long long i = k + (long long)K * g;
-      const double mh = (double)d.Mhat[i];
-      D += mh_cell(Mat(d, i), mh, mh + dp * (double)d.E[n + (long long)N * g]);
+      const double mh = (double)Mh[i];
+      const double m = normal ? (double)d.Mr[i] : (double)d.Mi[i];
+      D += mh_cell(m, mh, mh + dp * (double)Ev[n + (long long)N * g]);
     }
   }
   sm[gy * KX + kx] = D;
@@ -237,27 +253,33 @@ __global__ void k_p_pass2(Dev<T> d, int n) {
   }
 }
 
-// k_p_draw: finish the reduction, form the conditional (or proposal) moments, draw.
+// k_p_draw: finish the reduction over genome chunks (a warp per mutation type, fixed
+// butterfly order), form the conditional (or proposal) moments, draw.
 template <typename T>
 __global__ void k_p_draw(Dev<T> d, int n) {
   const int K = d.K, N = d.N;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
   const int iter = d.ctrl->iter;
   const int An = d.A[n];
   const long long c = k + (long long)K * n;
+  const bool zero_row = d.nzE[((iter - 1) & 1) * N + n] == 0;   // all(E[n, ] == 0), R/sample_Pn.R:56
+  double num1 = 0.0, den = 0.0;
+  if (An != 0 && !zero_row) {
+    for (int ch = lane; ch < d.n_gchunks; ch += 32) {
+      const double* pp = d.ppart + ((long long)ch * K + k) * 2;
+      num1 += pp[0]; den += pp[1];
+    }
+    num1 = warp_sum(num1); den = warp_sum(den);
+  }
+  if (lane != 0) return;
   const double Pold = (double)d.P[c];
   const Stream st = make_stream(d.seed, iter, PUR_P, c);
-  const bool zero_row = d.nzE[((iter - 1) & 1) * N + n] == 0;   // all(E[n, ] == 0), R/sample_Pn.R:56
   double x;
   if (An == 0 || zero_row) {
     x = prior_draw(d, st, 0, c);
   } else {
-    double num1 = 0.0, den = 0.0;
-    for (int ch = 0; ch < d.n_gchunks; ++ch) {
-      const double* pp = d.ppart + ((long long)ch * K + k) * 2;
-      num1 += pp[0]; den += pp[1];
-    }
     double mu, v;
     if (d.prior == PRIOR_EXPONENTIAL) {
       mu = (num1 - (double)d.Lambda_p[c]) / den; v = 1.0 / den;
@@ -284,11 +306,14 @@ __global__ void k_p_draw(Dev<T> d, int n) {
 template <typename T>
 __global__ void k_p_accept(Dev<T> d, int n) {
   const int K = d.K;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K || d.A[n] == 0) return;
   const long long c = k + (long long)K * n;
   double D = 0.0;
-  for (int ch = 0; ch < d.n_gchunks; ++ch) D += d.ppart[((long long)ch * K + k) * 2];
+  for (int ch = lane; ch < d.n_gchunks; ch += 32) D += d.ppart[((long long)ch * K + k) * 2];
+  D = warp_sum(D);
+  if (lane != 0) return;
   const double ratio = mh_ratio(D);
   d.P_acc[c] = (T)ratio;
   const double u = u01<double>(make_stream(d.seed, d.ctrl->iter, PUR_MH_P, c).at(0).x);
@@ -345,10 +370,10 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev) {
       double num1 = 0.0, den = 0.0;
       for (int k = lane; k < K; k += 32) {
         const double mh = Mh[k], p = Pn[k];
-        const double s = normal ? sg : mh;
+        const double inv = 1.0 / (normal ? sg : mh);
         const double mh_no = mh - p * Eold;
-        num1 += p * ((Mv[k] - mh_no) / s);
-        den += (p * p) * (1.0 / s);
+        num1 += p * ((Mv[k] - mh_no) * inv);
+        den += (p * p) * inv;
       }
       num1 = warp_sum(num1); den = warp_sum(den);
       double mu, v;
