@@ -506,14 +506,12 @@ struct Sampler : bnmf_handle {
     const int keepP = (have & BNMF_HAVE_P) ? 1 : 0, keepE = (have & BNMF_HAVE_E) ? 1 : 0;
     k_pside<T, 128><<<cfg.N, 128, 0, stream>>>(d, from_prior, keepP); ++launches;
     k_eside<T, 256><<<d.n_eblocks, 256, 0, stream>>>(d, from_prior, keepE); ++launches;
-    if (allreduce_buf(d.rowsumE_fx, cfg.N, NCCL_INT64, NCCL_SUM)) return 1;
     if (from_prior) { k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); ++launches; }
     else if (cfg.learning_rank) { if (rank_sweep()) return 1; }
     if (!(from_prior && (have & BNMF_HAVE_Z))) {
       if (z0) CK(cudaEventRecord(z0, stream));
       if (z_dispatch(false)) return 1; ++launches;
       if (z1) CK(cudaEventRecord(z1, stream));
-      if (allreduce_buf(d.SP, (size_t)cfg.K * cfg.N, NCCL_UINT64, NCCL_SUM)) return 1;
     } else {
       if (refresh_metrics_only()) return 1;
     }
@@ -526,9 +524,19 @@ struct Sampler : bnmf_handle {
   int p_kx = 32, p_gy = 8, p_ktiles = 1, col_blocks = 1, e_wpb = 8; size_t e_smem = 0;
   double* asum = nullptr; double sig_alpha = 3.0, sig_beta = 3.0;
 
+  // End of an iteration.  Sharded runs sum everything the next iteration (SP, rowSums(E):
+  // read by k_pside) and this iteration's metrics row need in ONE grouped NCCL operation:
+  // the payload is ~16 KB, so the cost of the exchange is its latency, paid once.
   int finish_iteration() {
     k_reduce_partials<T, 256><<<RED_BLOCKS, 256, 0, stream>>>(d, red_slices, red_ticket); ++launches;
-    if (allreduce_red()) return 1;
+    if (world > 1) {
+      const bool stats = cfg.likelihood == BNMF_POISSON && !cfg.MH;
+      if (stats) g_nccl.GroupStart();
+      int rc = stats ? allreduce_stats() : 0;
+      if (!rc) rc = allreduce_red();
+      if (stats) { const int r = g_nccl.GroupEnd(); if (!rc && r) rc = fail("ncclGroupEnd: %s", g_nccl.GetErrorString(r)); }
+      if (rc) return 1;
+    }
     k_metrics<T><<<1, 32, 0, stream>>>(d); ++launches;
     return 0;
   }

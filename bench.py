@@ -107,6 +107,10 @@ def synth(w, seed=0):
 
 # ------------------------------------------------------------------------------------------
 def run_b200(args):
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version
+    # banner, torchrun notices) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from bayesnmf_b200.shard import shard_bounds, sharded_handle
@@ -235,6 +239,8 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(res), flush=True)
 
