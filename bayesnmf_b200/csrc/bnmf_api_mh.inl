@@ -28,8 +28,8 @@ template <typename T> int Sampler<T>::mh_setup() {
   p_kx = ((K + 31) / 32) * 32; if (p_kx > 128) p_kx = 128;
   p_gy = 256 / p_kx; if (p_gy < 1) p_gy = 1;
   p_ktiles = (K + p_kx - 1) / p_kx;
-  long long chunks = (G + (long long)p_gy * 8 - 1) / ((long long)p_gy * 8);
-  const long long cap = std::max(1, 592 / p_ktiles);
+  long long chunks = (G + 63) / 64;                       // at least 64 genomes per block
+  const long long cap = std::max(1, 2368 / p_ktiles);     // up to 16 blocks per SM: the passes are latency-bound
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   d.gchunk = (int)((G + chunks - 1) / chunks);

@@ -292,7 +292,10 @@ __device__ __forceinline__ void zstat_quad(const U4& w, const T* col, T tots, in
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     pp[p] = 0;
-    if (ALL4 || p < lim) pp[p] = min(cdf_search<T, NP>(col, pick_threshold(ww[p], tots)), N - 1);
+    if (ALL4 || p < lim) {
+      pp[p] = cdf_search<T, NP>(col, pick_threshold(ww[p], tots));
+      if (sizeof(T) == 4) pp[p] = min(pp[p], N - 1);   // float: t can round up to the total; double: t < total always
+    }
   }
   bool a1 = lim > 1, a2 = lim > 2, a3 = lim > 3;
   int i0 = 1, i1 = 1, i2 = 1;

@@ -31,6 +31,7 @@ WORKLOADS = {
     "c3": dict(K=96, G=100000, N=20, likelihood="poisson", prior="gamma", MH=False, mu_T=4000.0),
     "c3-exome": dict(K=96, G=100000, N=20, likelihood="poisson", prior="gamma", MH=False, mu_T=100.0),
 }
+# the other BASELINE.json configurations, timed by tools/time_configs.py (not bench lines)
 METRIC = "Gibbs iterations/s (Poisson-Gamma, K=96, G=100000, N=20)"
 L2_FLUSH_BYTES = 512 << 20
 
