@@ -504,8 +504,19 @@ struct Sampler : bnmf_handle {
   int mh_iteration(int from_prior, uint32_t have);
   int poisson_iteration(int from_prior, uint32_t have, cudaEvent_t z0, cudaEvent_t z1) {
     const int keepP = (have & BNMF_HAVE_P) ? 1 : 0, keepE = (have & BNMF_HAVE_E) ? 1 : 0;
-    k_pside<T, 128><<<cfg.N, 128, 0, stream>>>(d, from_prior, keepP); ++launches;
-    k_eside<T, 256><<<d.n_eblocks, 256, 0, stream>>>(d, from_prior, keepE); ++launches;
+    // instantiated per (prior, prior draw or not): halves the code each launch has to fetch
+    const int var = (cfg.prior == BNMF_GAMMA ? 2 : 0) | (from_prior ? 1 : 0);
+    switch (var) {
+      case 0: k_pside<T, 128, PRIOR_EXPONENTIAL, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
+              k_eside<T, 256, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+      case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
+              k_eside<T, 256, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+      case 2: k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
+              k_eside<T, 256, PRIOR_GAMMA, 0><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+      default: k_pside<T, 128, PRIOR_GAMMA, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
+               k_eside<T, 256, PRIOR_GAMMA, 1><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+    }
+    launches += 2;
     if (from_prior) { k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); ++launches; }
     else if (cfg.learning_rank) { if (rank_sweep()) return 1; }
     if (!(from_prior && (have & BNMF_HAVE_Z))) {

@@ -67,8 +67,9 @@ __global__ void k_begin_iter(Dev<T> d, int* work_ctr, int n_ctr) {
 // from_prior = 1 draws P from its prior (R/sample_Pn.R:12-30) and skips the
 // hyper-updates; keepP = 1 leaves a user-supplied P untouched (skip = names(init_params)).
 // ------------------------------------------------------------------------------
-template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int from_prior, int keepP) {
+template <typename T, int THREADS, int PRIOR, int FROM_PRIOR>
+__global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
+  constexpr int from_prior = FROM_PRIOR;
   __shared__ double scratch[THREADS / 32];
   const int n = blockIdx.x;
   const int K = d.K, N = d.N;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int from_prior, int
     double Pold = (double)d.P[c];
     double Pnew = Pold;
     double lpc = 0.0;
-    if (d.prior == PRIOR_GAMMA) {
+    if (PRIOR == PRIOR_GAMMA) {
       double al = (double)d.Alpha_p[c], be = (double)d.Beta_p[c];
       if (!from_prior) {
         be = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_P1, c),
@@ -134,8 +135,9 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int from_prior, int
 //   rowSums(E) (fixed point, order-independent), sum log prior(E)   (R/utils.R:168-173)
 // Consumes and clears SE.  Block b writes its partial to epart[b].
 // ------------------------------------------------------------------------------
-template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int from_prior, int keepE) {
+template <typename T, int THREADS, int PRIOR, int FROM_PRIOR>
+__global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
+  constexpr int from_prior = FROM_PRIOR;
   __shared__ double scratch[THREADS / 32];
   __shared__ long long fx[THREADS];
   const int N = d.N;
@@ -145,46 +147,58 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int from_prior, int
   const int iter = d.ctrl->iter;
   double lp = 0.0;
   long long myfx = 0;
-  if (idx < cells) {
-    const int n = (int)(idx % N);
-    const long long gl = idx / N;
+  // Threads past the end redo the last cell (and store nothing) so that the whole block runs the
+  // same stages; the barriers between the stages keep the eight warps of a block inside the
+  // same stretch of code -- the samplers are long, and a block whose warps drift apart
+  // stalls on instruction fetch.
+  const bool act = idx < cells;
+  const long long ii = act ? idx : cells - 1;
+  {
+    const int n = (int)(ii % N);
+    const long long gl = ii / N;
     const long long c = (long long)n + (long long)N * (d.g0 + gl);  // global cell id
     const int An = d.A[n];
     const double csP = An ? (double)d.colsumP[n] : 0.0;
-    double Eold = (double)d.E[idx], Enew = Eold;
-    if (d.prior == PRIOR_GAMMA) {
-      double al = (double)d.Alpha_e[idx], be = (double)d.Beta_e[idx];
+    double Eold = (double)d.E[ii], Enew = Eold;
+    if (PRIOR == PRIOR_GAMMA) {
+      double al = (double)d.Alpha_e[ii], be = (double)d.Beta_e[ii];
       if (!from_prior) {
         be = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
-                                (double)d.A_e.at(idx) + al, (double)d.B_e.at(idx) + Eold);
-        al = alpha_draw(make_stream(d.seed, iter, PUR_HYP_E2, c),
-                        (double)d.C_e.at(idx), (double)d.D_e.at(idx), be, Eold, al);
-        d.Beta_e[idx] = (T)be; d.Alpha_e[idx] = (T)al;
+                                (double)d.A_e.at(ii) + al, (double)d.B_e.at(ii) + Eold);
+        __syncthreads();
+        al = alpha_draw<true>(make_stream(d.seed, iter, PUR_HYP_E2, c),
+                              (double)d.C_e.at(ii), (double)d.D_e.at(ii), be, Eold, al);
+        __syncthreads();
+        if (act) { d.Beta_e[ii] = (T)be; d.Alpha_e[ii] = (T)al; }
       }
       if (!keepE) {
         double shape = al, rate = be;
-        if (!from_prior) { shape += (double)d.SE[idx]; rate += csP; }
+        if (!from_prior) { shape += (double)d.SE[ii]; rate += csP; }
         Enew = gamma_draw<double>(make_stream(d.seed, iter, PUR_E, c), shape, rate);
       }
+      __syncthreads();
       lp = dgamma_log((double)(T)Enew, (double)(T)al, (double)(T)be);
     } else {
-      double la = (double)d.Lambda_e[idx];
+      double la = (double)d.Lambda_e[ii];
       if (!from_prior) {
         la = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
-                                (double)d.A_e.at(idx) + 1.0, (double)d.B_e.at(idx) + Eold);
-        d.Lambda_e[idx] = (T)la;
+                                (double)d.A_e.at(ii) + 1.0, (double)d.B_e.at(ii) + Eold);
+        __syncthreads();
+        if (act) d.Lambda_e[ii] = (T)la;
       }
       if (!keepE) {
         double shape = 1.0, rate = la;
-        if (!from_prior) { shape += (double)d.SE[idx]; rate += csP; }
+        if (!from_prior) { shape += (double)d.SE[ii]; rate += csP; }
         Enew = gamma_draw<double>(make_stream(d.seed, iter, PUR_E, c), shape, rate);
       }
       lp = dexp_log((double)(T)Enew, (double)(T)la);
     }
-    d.E[idx] = (T)Enew;
-    d.SE[idx] = 0;
-    if (d.ring_cap > 0) d.ring_E[(long long)d.ctrl->ring_pos * cells + idx] = (T)Enew;
-    myfx = llrint((double)(T)Enew * RS_FX);
+    if (act) {
+      d.E[ii] = (T)Enew;
+      d.SE[ii] = 0;
+      if (d.ring_cap > 0) d.ring_E[(long long)d.ctrl->ring_pos * cells + ii] = (T)Enew;
+      myfx = llrint((double)(T)Enew * RS_FX);
+    } else lp = 0.0;
   }
   fx[threadIdx.x] = myfx;
   double lps = block_sum<THREADS>(lp, scratch);   // contains __syncthreads => fx visible

@@ -20,8 +20,12 @@
 
 #if defined(__CUDACC__)
 #define BNMF_HD __host__ __device__ __forceinline__
+// the big samplers are called, not inlined: a kernel that inlines three gamma draws and an
+// adaptive-rejection draw is ~140 KB of straight-line code and stalls on instruction fetch
+#define BNMF_HD_CALL __host__ __device__ __noinline__
 #else
 #define BNMF_HD inline
+#define BNMF_HD_CALL inline
 #endif
 
 namespace bnmf {
@@ -134,7 +138,7 @@ template <typename T> BNMF_HD T normal_draw(const Stream& s, T mean, T sd) {
 // uniform, w -> boost uniform.  Result floored at the smallest normal so that a
 // later log() stays finite (R's rgamma can return exactly 0 for tiny shapes).
 // (stats::rgamma(n, shape, rate): R/sample_Pn.R:23-27,116-118, R/sample_priors.R:285-344)
-template <typename T> BNMF_HD T gamma_draw(const Stream& s, T shape, T rate, uint32_t sub0 = 0) {
+template <typename T> BNMF_HD_CALL T gamma_draw(const Stream s, T shape, T rate, uint32_t sub0 = 0) {
   const bool boost = shape < (T)1;
   const T a = boost ? shape + (T)1 : shape;
   const T d = a - (T)(1.0 / 3.0);
@@ -169,7 +173,7 @@ template <typename T> BNMF_HD T gamma_draw(const Stream& s, T shape, T rate, uin
 //                   formed as sd*(z-alpha) directly so a mean far below zero does
 //                   not cancel catastrophically.
 // Attempt t consumes Philox block t: (x,y) -> normal or (x -> exp, y -> accept).
-template <typename T> BNMF_HD T truncnorm0_draw(const Stream& s, T mean, T sd) {
+template <typename T> BNMF_HD_CALL T truncnorm0_draw(const Stream s, T mean, T sd) {
   const T alpha = -mean / sd;
   if (alpha <= (T)0.45) {
     T z = alpha;
@@ -194,7 +198,7 @@ template <typename T> BNMF_HD T truncnorm0_draw(const Stream& s, T mean, T sd) {
 
 // ---- digamma / trigamma (recurrence to x >= 6, then asymptotic series) ----------
 // Evaluated together: the Newton step on h' needs both and they share every reciprocal.
-template <typename T> BNMF_HD void digamma_trigamma(T x, T& psi, T& tri) {
+template <typename T> BNMF_HD_CALL void digamma_trigamma(T x, T& psi, T& tri) {
   T r1 = (T)0, r2 = (T)0;
   while (x < (T)6) {
     const T inv = (T)1 / x;
@@ -226,7 +230,7 @@ template <typename T> BNMF_HD T trigamma(T x) { T p, t; digamma_trigamma<T>(x, p
 // mode-s, mode, mode+s, s = Laplace sd), i.e. non-adaptive ARS.  Any choice of
 // tangent points gives a valid envelope; only the acceptance rate depends on them.
 struct AlphaTarget { double cm1, b; };
-BNMF_HD double alpha_h(const AlphaTarget& t, double x) { return t.cm1 * log(x) - t.b * x - lgamma(x); }
+BNMF_HD_CALL double alpha_h(const AlphaTarget t, double x) { return t.cm1 * log(x) - t.b * x - lgamma(x); }
 BNMF_HD double alpha_hp(const AlphaTarget& t, double x) { return t.cm1 / x - t.b - digamma<double>(x); }
 BNMF_HD double alpha_hpp(const AlphaTarget& t, double x) { return -t.cm1 / (x * x) - trigamma<double>(x); }
 BNMF_HD void alpha_hp_hpp(const AlphaTarget& t, double x, double& f, double& fp) {
@@ -263,7 +267,15 @@ BNMF_HD double seg_inv(double s, double a, double b, double q) {
 // very conditional one sweep ago, hence within about one standard deviation of the mode).
 // The mode is only needed approximately: any three increasing tangent points give a valid
 // envelope of a concave log-density, their position only moves the acceptance rate.
-BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, double X, double x0) {
+// STAGES = true (device, every thread of the block calls it): block barriers between the mode
+// search, the envelope and the rejection loop keep the warps of a block in the same code.
+#if defined(__CUDA_ARCH__)
+#define BNMF_STAGE() do { if (STAGES) __syncthreads(); } while (0)
+#else
+#define BNMF_STAGE() do { } while (0)
+#endif
+template <bool STAGES = false>
+BNMF_HD_CALL double alpha_draw(const Stream st, double C, double D, double beta, double X, double x0) {
   const double LO = 1e-3, HI = 1e4;
   AlphaTarget t; t.cm1 = C - 1.0; t.b = D - log(beta) - log(X);
   // --- approximate mode: safeguarded Newton on h' (strictly decreasing) to BNMF_ALPHA_TOL ---
@@ -286,6 +298,7 @@ BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, dou
     }
     m = x;
   }
+  BNMF_STAGE();
   double hp_m, hpp_m;
   alpha_hp_hpp(t, m, hp_m, hpp_m);
   double s = 1.0 / sqrt(-hpp_m);
@@ -329,6 +342,7 @@ BNMF_HD double alpha_draw(const Stream& st, double C, double D, double beta, dou
     mass[j] = (z[j + 1] > z[j]) ? exp(top[j] - hmax) * seg_unit(sl[j], z[j + 1] - z[j]) : 0.0;
     tot += mass[j];
   }
+  BNMF_STAGE();
   double x = m;
   for (uint32_t a = 0; a < 4096u; ++a) {
     U4 w = st.at(a);
