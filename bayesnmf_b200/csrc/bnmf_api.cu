@@ -140,6 +140,7 @@ template <typename T> static __global__ void k_hist_copy(Dev<T> d, T* P_hist, in
   if (A_hist && i < d.N) A_hist[row * d.N + i] = d.A[i];
 }
 
+constexpr int ET = 512;   // threads per block of k_eside
 enum StType { ST_T, ST_I32, ST_U64 };
 struct StEntry { void* p; long long len; StType ty; };
 
@@ -265,7 +266,7 @@ struct Sampler : bnmf_handle {
     while (ZR > 1 && (long long)cts * ((K + ZR - 1) / ZR) < 16LL * 148 * 16) ZR >>= 1;
     if (ZR > KT) ZR = KT;
     d.n_zitems = cts * n_ktiles * ((KT + ZR - 1) / ZR);
-    d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, 256);
+    d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, ET);
     if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + 2 * N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
         dalloc(&d.red, PC_COLS) || dalloc(&work_ctr, n_ktiles + 8) || dalloc(&nanflags, 5 * N)) return 1;
     if (dalloc(&d.ctrl, 1) || dalloc(&red_slices, RED_BLOCKS * PC_COLS) || dalloc(&red_ticket, 1)) return 1;
@@ -508,13 +509,13 @@ struct Sampler : bnmf_handle {
     const int var = (cfg.prior == BNMF_GAMMA ? 2 : 0) | (from_prior ? 1 : 0);
     switch (var) {
       case 0: k_pside<T, 128, PRIOR_EXPONENTIAL, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              k_eside<T, 256, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+              k_eside<T, ET, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
       case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              k_eside<T, 256, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+              k_eside<T, ET, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
       case 2: k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              k_eside<T, 256, PRIOR_GAMMA, 0><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+              k_eside<T, ET, PRIOR_GAMMA, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
       default: k_pside<T, 128, PRIOR_GAMMA, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
-               k_eside<T, 256, PRIOR_GAMMA, 1><<<d.n_eblocks, 256, 0, stream>>>(d, keepE); break;
+               k_eside<T, ET, PRIOR_GAMMA, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
     }
     launches += 2;
     if (from_prior) { k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); ++launches; }
