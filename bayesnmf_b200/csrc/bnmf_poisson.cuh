@@ -85,10 +85,11 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
     if (PRIOR == PRIOR_GAMMA) {
       double al = (double)d.Alpha_p[c], be = (double)d.Beta_p[c];
       if (!from_prior) {
-        be = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_P1, c),
-                                (double)d.A_p.at(c) + al, (double)d.B_p.at(c) + Pold);
-        al = alpha_draw(make_stream(d.seed, iter, PUR_HYP_P2, c),
-                        (double)d.C_p.at(c), (double)d.D_p.at(c), be, Pold, al);
+        // (double)(T): every later use sees the value as stored in the state precision
+        be = (double)(T)gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_P1, c),
+                                           (double)d.A_p.at(c) + al, (double)d.B_p.at(c) + Pold);
+        al = (double)(T)alpha_draw(make_stream(d.seed, iter, PUR_HYP_P2, c),
+                                   (double)d.C_p.at(c), (double)d.D_p.at(c), be, Pold, al);
         d.Beta_p[c] = (T)be; d.Alpha_p[c] = (T)al;
       }
       if (!keepP) {
@@ -100,8 +101,8 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
     } else {  // PRIOR_EXPONENTIAL
       double la = (double)d.Lambda_p[c];
       if (!from_prior) {
-        la = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_P1, c),
-                                (double)d.A_p.at(c) + 1.0, (double)d.B_p.at(c) + Pold);
+        la = (double)(T)gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_P1, c),
+                                           (double)d.A_p.at(c) + 1.0, (double)d.B_p.at(c) + Pold);
         d.Lambda_p[c] = (T)la;
       }
       if (!keepP) {
@@ -163,11 +164,11 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
     if (PRIOR == PRIOR_GAMMA) {
       double al = (double)d.Alpha_e[ii], be = (double)d.Beta_e[ii];
       if (!from_prior) {
-        be = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
-                                (double)d.A_e.at(ii) + al, (double)d.B_e.at(ii) + Eold);
+        be = (double)(T)gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
+                                           (double)d.A_e.at(ii) + al, (double)d.B_e.at(ii) + Eold);
         __syncthreads();
-        al = alpha_draw<true>(make_stream(d.seed, iter, PUR_HYP_E2, c),
-                              (double)d.C_e.at(ii), (double)d.D_e.at(ii), be, Eold, al);
+        al = (double)(T)alpha_draw<true>(make_stream(d.seed, iter, PUR_HYP_E2, c),
+                                         (double)d.C_e.at(ii), (double)d.D_e.at(ii), be, Eold, al);
         __syncthreads();
         if (act) { d.Beta_e[ii] = (T)be; d.Alpha_e[ii] = (T)al; }
       }
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
     } else {
       double la = (double)d.Lambda_e[ii];
       if (!from_prior) {
-        la = gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
-                                (double)d.A_e.at(ii) + 1.0, (double)d.B_e.at(ii) + Eold);
+        la = (double)(T)gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
+                                           (double)d.A_e.at(ii) + 1.0, (double)d.B_e.at(ii) + Eold);
         __syncthreads();
         if (act) d.Lambda_e[ii] = (T)la;
       }

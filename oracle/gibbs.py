@@ -93,14 +93,16 @@ def get_temp_sched(length, n_temp, rng=None):
 # --------------------------------------------------------------------------------------
 # latent counts  (R/sample_params.R:253-265)
 # --------------------------------------------------------------------------------------
-def z_cdf(P, A, E):
-    """Running CDF of p_n = P[k,n] A_n E[n,g], accumulated sequentially over n."""
-    Pa = np.where(np.asarray(A).reshape(1, -1) != 0, P, 0.0)
-    prob = Pa[:, :, None] * E[None, :, :]          # K x N x G
-    return np.cumsum(prob, axis=1)                 # sequential adds, no pairwise
+def z_cdf(P, A, E, f32=False):
+    """Running CDF of p_n = P[k,n] A_n E[n,g], accumulated sequentially over n (in float32
+    arithmetic, one rounding per multiply and per add, for the float state of BNMF_F32)."""
+    dt = np.float32 if f32 else np.float64
+    Pa = np.where(np.asarray(A).reshape(1, -1) != 0, P, 0.0).astype(dt)
+    prob = Pa[:, :, None] * np.asarray(E).astype(dt)[None, :, :]     # K x N x G
+    return np.add.accumulate(prob, axis=1, dtype=dt)                # sequential adds, no pairwise
 
 
-def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_000_000):
+def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_000_000, f32=False):
     """sample_Zkg for every cell, reduced to SP = sum_g Z (K x N), SE = sum_k Z (N x G).
 
     Reference: probs_n = P[k,n]*A[1,n]*E[n,g]; all-zero -> Z = 0; else
@@ -111,7 +113,7 @@ def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_
     M = np.asarray(M)
     K, G = M.shape
     N = P.shape[1]
-    cdf = z_cdf(P, A, E)                           # K x N x G
+    cdf = z_cdf(P, A, E, f32)                      # K x N x G
     total = cdf[:, -1, :]                          # K x G  == Mhat
     Mi = M.astype(np.int64)
     work = (Mi > 0) & (total > 0.0)
@@ -139,7 +141,10 @@ def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_
         word = W[j & 3, np.arange(len(owner))]
         # t = (w + 0.5) * (total * 2^-32): the same number as u01(w) * total (power-of-two
         # scaling is exact), written the way the kernel evaluates it
-        if bits == 32:
+        if f32:     # float state: 24 random bits, float32 arithmetic throughout
+            tots = total[kk[owner], gg[owner]] * np.float32(2.0 ** -24)
+            t = ((word >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * tots
+        elif bits == 32:
             t = (word.astype(np.float64) + 0.5) * (total[kk[owner], gg[owner]] * 2.0 ** -32)
         else:
             t = ((word >> np.uint32(8)).astype(np.float64) + 0.5) * (total[kk[owner], gg[owner]] * 2.0 ** -24)
@@ -216,6 +221,22 @@ def get_MAP(P_list, E_list, A_list):
     return acc_P / len(idx), acc_E / len(idx), A_map, idx
 
 
+class _Store(dict):
+    """State container that rounds every stored float array to float32 when emulating the
+    BNMF_F32 state precision (the kernels compute in double and store T)."""
+
+    def __init__(self, f32, *a, **kw):
+        self.f32 = f32
+        super().__init__()
+        for k, v in dict(*a, **kw).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        if self.f32 and isinstance(v, np.ndarray) and v.dtype == np.float64:
+            v = v.astype(np.float32).astype(np.float64)
+        super().__setitem__(k, v)
+
+
 class OracleSampler:
     """State + one-iteration update of bayesNMF_sampler (R/bayesNMF_sampler.R:8-747),
     restricted to what the hot path touches."""
@@ -223,7 +244,8 @@ class OracleSampler:
     def __init__(self, data, N, likelihood="poisson", prior="truncnormal", MH=None,
                  learning_rank=False, rank_method="SBFI", seed=0,
                  hyperprior_params=None, init_prior_params=None, init_params=None,
-                 temperature_schedule=None, g0=0, G_total=None, mean_data=None, bits=32, reduce_fn=None):
+                 temperature_schedule=None, g0=0, G_total=None, mean_data=None, bits=32, reduce_fn=None,
+                 state="f64"):
         self.data = np.asarray(data, dtype=np.float64)
         self.K, self.G = self.data.shape
         self.N = int(N)
@@ -232,6 +254,8 @@ class OracleSampler:
         check_model(likelihood, prior, self.MH)
         self.learning_rank, self.rank_method = bool(learning_rank), rank_method
         self.seed, self.bits = int(seed), bits
+        self.f32 = state == "f32"          # BNMF_F32: state stored as float, arithmetic in double
+        self._r = (lambda x: np.asarray(x, dtype=np.float64).astype(np.float32).astype(np.float64)) if self.f32 else (lambda x: x)
         self.g0 = int(g0)
         self.G_total = int(G_total) if G_total is not None else self.G
         # genome-sharded runs (Poisson latent-count models): `reduce_fn(array) -> array` sums an
@@ -245,7 +269,7 @@ class OracleSampler:
         # fill_hyperprior_params_  (R/setup.R:15-88): scalars broadcast to matrices
         hp = default_hyperprior_params(prior, mean_data, self.N)
         hp.update(hyperprior_params or {})
-        self.hyper = {}
+        self.hyper = _Store(self.f32)
         names = {"truncnormal": "MSAB", "exponential": "AB", "gamma": "ABCD"}[prior]
         for nm in names:
             for end, shp in (("_p", (self.K, self.N)), ("_e", (self.N, self.G))):
@@ -254,8 +278,8 @@ class OracleSampler:
                     self.hyper[full] = np.asarray(hp[full], dtype=np.float64).reshape(shp)
                 else:
                     self.hyper[full] = np.full(shp, float(hp[full.lower()]))
-        self.prior_params = {k: np.array(v, dtype=np.float64) for k, v in (init_prior_params or {}).items()}
-        self.params = {k: np.array(v, dtype=np.float64) for k, v in (init_params or {}).items()}
+        self.prior_params = _Store(self.f32, {k: np.array(v, dtype=np.float64) for k, v in (init_prior_params or {}).items()})
+        self.params = _Store(self.f32, {k: np.array(v, dtype=np.float64) for k, v in (init_params or {}).items()})
         self.acc = {"P": np.full((self.K, self.N), np.nan), "E": np.full((self.N, self.G), np.nan)}
         self.SP = np.zeros((self.K, self.N), dtype=np.int64)
         self.SE = np.zeros((self.N, self.G), dtype=np.int64)
@@ -495,7 +519,7 @@ class OracleSampler:
     def sample_En_poisson(self, n):
         """R/sample_En.R:97-119: Gamma(shape + sum_k Z[k,n,g], rate + A_n sum_k P[k,n])."""
         pp, A, P = self.prior_params, self.params["A"], self.params["P"]
-        csP = P[:, n].sum()
+        csP = float(self._r(P[:, n].sum()))        # colSums(P) is stored in the state precision
         if self.prior == "gamma":
             shape = pp["Alpha_e"][n, :] + self.SE[n, :]
             rate = pp["Beta_e"][n, :] + A[n] * csP
@@ -689,10 +713,10 @@ class OracleSampler:
         if "P" not in skip:
             self._rsE_cache = None
             for n in range(self.N):
-                p["P"][:, n] = self.sample_Pn(n, from_prior)
+                p["P"][:, n] = self._r(self.sample_Pn(n, from_prior))
         if "E" not in skip:
             for n in range(self.N):
-                p["E"][n, :] = self.sample_En(n, from_prior)
+                p["E"][n, :] = self._r(self.sample_En(n, from_prior))
         if "A" not in skip and self.learning_rank:
             p["R"] = self.sample_R(from_prior)
             for n in range(self.N):
@@ -701,7 +725,7 @@ class OracleSampler:
             p["A"] = np.ones(self.N)
         if self.likelihood == "poisson" and not self.MH and "Z" not in skip:
             self.SP, self.SE = sample_Z_stats(self.data, p["P"], p["A"], p["E"], self.seed, self.iter,
-                                              g0=self.g0, bits=self.bits)
+                                              g0=self.g0, bits=self.bits, f32=self.f32)
             self.SP = self.reduce(self.SP)
         if self.likelihood == "normal" and "sigmasq" not in skip:
             p["sigmasq"] = self.sample_sigmasq()

@@ -114,3 +114,43 @@ def test_default_hyperparameters(built_lib, lik, prior, MH):
     o.step(); h.step(1)
     np.testing.assert_allclose(h.get_state("P"), o.params["P"], rtol=1e-6, atol=1e-300)
     np.testing.assert_allclose(h.get_state("E"), o.params["E"], rtol=1e-6, atol=1e-300)
+
+
+@pytest.mark.parametrize("K,G,N,mu", [(96, 100, 20, 4000.0), (130, 77, 7, 300.0), (96, 300, 40, 100.0)])
+def test_zstat_bit_exact_f32_state(built_lib, K, G, N, mu):
+    """BNMF_F32: state and CDF in float32, 24 random bits per pick -- still bit-exact against
+    the oracle's float32 restatement of the same arithmetic."""
+    from oracle.gibbs import sample_Z_stats
+    rng = np.random.default_rng(K + G + N)
+    M, _, _ = synth_counts(K, G, N, mu, seed=1)
+    P = rng.gamma(1.0, 0.02, size=(K, N)).astype(np.float32).astype(np.float64)
+    E = rng.gamma(1.0, mu / N, size=(N, G)).astype(np.float32).astype(np.float64)
+    A = np.ones(N); A[1] = 0
+    h = _handle(M, N, precision="f32")
+    h.set_state("P", P); h.set_state("E", E); h.set_state("A", A)
+    h.sample_z(5)
+    oSP, oSE = sample_Z_stats(M, P, A, E, seed=3, it=5, f32=True)
+    assert np.array_equal(h.get_state("SP"), oSP) and np.array_equal(h.get_state("SE"), oSE)
+
+
+@pytest.mark.parametrize("prior", ["gamma", "exponential"])
+def test_iteration_parity_f32_state(built_lib, prior):
+    """Full iterations with float32 state: every stored quantity equals the oracle's float32
+    emulation to 1e-6 (identical floats up to draws that land on a rounding boundary), margins
+    bit-exact, metrics to 1e-5 (they are formed from the float32 CDF total)."""
+    from oracle.gibbs import OracleSampler
+    K, G, N = 96, 64, 5
+    M, _, _ = synth_counts(K, G, N, 2000.0, seed=5)
+    o = OracleSampler(M, N, "poisson", prior, MH=False, seed=9, state="f32")
+    h = _handle(M, N, prior=prior, seed=9, precision="f32")
+    h.init_from_prior()
+    names = ["P", "E"] + (["Alpha_p", "Beta_p", "Alpha_e", "Beta_e"] if prior == "gamma" else ["Lambda_p", "Lambda_e"])
+    for it in range(4):
+        om = o.step()
+        met = h.step(1)["metrics"][0]
+        for nm in names:
+            ref = o.params[nm] if nm in o.params else o.prior_params[nm]
+            np.testing.assert_allclose(h.get_state(nm), ref, rtol=1e-6, atol=1e-300, err_msg=f"iter {o.iter} {nm}")
+        assert np.array_equal(h.get_state("SP"), o.SP) and np.array_equal(h.get_state("SE"), o.SE)
+        for j, key in ((1, "RMSE"), (2, "KL"), (3, "loglikelihood"), (4, "logposterior")):
+            np.testing.assert_allclose(met[j], om[key], rtol=1e-5, err_msg=f"iter {o.iter} {key}")

@@ -127,3 +127,25 @@ def test_user_supplied_initial_values(built_lib):
     met = h.step(1)["metrics"][0]
     np.testing.assert_allclose(h.get_state("P"), o.params["P"], rtol=RTOL)
     np.testing.assert_allclose(met[3], om["loglikelihood"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("lik,prior,MH", [("poisson", "truncnormal", True), ("normal", "exponential", False)])
+def test_sweep_parity_f32_state(built_lib, lik, prior, MH):
+    """BNMF_F32 state for the sweep models: conditional draws within 1e-4 relative of the oracle's
+    float32-state emulation (north star: 1e-4 for fp32)."""
+    from bayesnmf_b200 import Handle
+    from oracle.gibbs import OracleSampler
+    K, G, N = 96, 64, 4
+    M, _, _ = synth_counts(K, G, N, 2000.0, seed=4)
+    if lik == "normal":
+        M = M + np.random.default_rng(0).normal(0, 2.0, M.shape)
+        M = M.astype(np.float32).astype(np.float64)          # the data are stored in the state precision too
+    o = OracleSampler(M, N, lik, prior, MH=MH, seed=6, state="f32")
+    h = Handle(M, N, likelihood=lik, prior=prior, MH=MH, seed=6, precision="f32")
+    h.init_from_prior()
+    for it in range(3):
+        om = o.step()
+        met = h.step(1)["metrics"][0]
+        np.testing.assert_allclose(h.get_state("P"), o.params["P"], rtol=1e-4, atol=1e-7, err_msg=f"iter {o.iter} P")
+        np.testing.assert_allclose(h.get_state("E"), o.params["E"], rtol=1e-4, atol=1e-5, err_msg=f"iter {o.iter} E")
+        np.testing.assert_allclose(met[3], om["loglikelihood"], rtol=1e-4)
