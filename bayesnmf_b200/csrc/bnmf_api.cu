@@ -287,10 +287,21 @@ struct Sampler : bnmf_handle {
     if (ensure_stage(KG)) return 1;
     CK(cudaMemcpyAsync(stage, data, (size_t)KG * sizeof(double), cudaMemcpyHostToDevice, stream));
     if (cfg.likelihood == BNMF_POISSON) {
-      for (long long i = 0; i < KG; ++i) {
-        double v = data[i];
-        if (!(v >= 0.0) || v != std::floor(v) || v > 2147483647.0)
-          return fail("bnmf_create: Poisson likelihood needs non-negative integer counts (data[%lld] = %g)", i, v);
+      // counts: non-negative integers; a cell below 2^24 and a genome (column) total below 2^31
+      // keep the quad offsets of k_zstat and the int32 margins SE exact
+      for (long long g = 0; g < G; ++g) {
+        double colsum = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const long long i = k + (long long)K * g;
+          const double v = data[i];
+          if (!(v >= 0.0) || v != std::floor(v))
+            return fail("bnmf_create: Poisson likelihood needs non-negative integer counts (data[%lld] = %g)", i, v);
+          if (v > 16777216.0)
+            return fail("bnmf_create: count %g at data[%lld] exceeds the supported 2^24 per cell", v, i);
+          colsum += v;
+        }
+        if (colsum >= 2147483648.0)
+          return fail("bnmf_create: column %lld sums to %g counts, the supported maximum is 2^31 - 1", g, colsum);
       }
       int32_t* mi; if (dalloc(&mi, KG)) return 1;
       k_cvt_in_i32<<<blocks(KG, 256), 256, 0, stream>>>(stage, mi, KG);

@@ -154,3 +154,15 @@ def test_iteration_parity_f32_state(built_lib, prior):
         assert np.array_equal(h.get_state("SP"), o.SP) and np.array_equal(h.get_state("SE"), o.SE)
         for j, key in ((1, "RMSE"), (2, "KL"), (3, "loglikelihood"), (4, "logposterior")):
             np.testing.assert_allclose(met[j], om[key], rtol=1e-5, err_msg=f"iter {o.iter} {key}")
+
+
+def test_count_limits_rejected(built_lib):
+    """Inputs the kernels cannot represent exactly fail loudly at creation."""
+    from bayesnmf_b200 import BnmfError
+    M = np.ones((8, 4))
+    for bad in (-1.0, 0.5, 2.0 ** 24 + 1, np.nan):
+        Mb = M.copy(); Mb[3, 2] = bad
+        with pytest.raises(BnmfError):
+            _handle(Mb, 2)
+    h = _handle(np.full((8, 4), 2.0 ** 24), 2)      # the largest supported cell
+    h.close()
