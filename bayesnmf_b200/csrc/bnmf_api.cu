@@ -251,13 +251,16 @@ struct Sampler : bnmf_handle {
     if (cfg.MH) { if (reg("P_acceptance_rate", &d.P_acc, KN) || reg("E_acceptance_rate", &d.E_acc, NG)) return 1; }
     if (cfg.MH || cfg.likelihood == BNMF_NORMAL || cfg.learning_rank) { if (reg("Mhat", &d.Mhat, KG)) return 1; }
 
-    // work decomposition of the column kernels: the k-tile is the largest multiple of 32
-    // rows (<= 128) whose P tile + accumulators fit next to the per-thread CDF/histogram
+    // work decomposition of the column kernels: K is cut into equal tiles whose P tile +
+    // accumulators fit next to the per-warp threshold / histogram tables
     NP = ((N + 3) / 4) * 4; if (NP > 32) NP = ((N + 7) / 8) * 8;
     const size_t z_budget = NP <= 32 ? (size_t)112 * 1024 : (size_t)226 * 1024;
-    KT = ((K + 31) / 32) * 32; if (KT > 128) KT = 128;
+    // equal K tiles (a multiple of 8 rows, at most 128), as few as fit the shared-memory budget
     const int zw = NP <= 32 ? 8 : 4;
-    while (KT > 32 && zstat_smem_bytes<T>(KT, NP, N, zw) > z_budget) KT -= 32;
+    for (int t = (K + 127) / 128; ; ++t) {
+      KT = (((K + t - 1) / t + 7) / 8) * 8;
+      if (KT <= 8 || zstat_smem_bytes<T>(KT, NP, N, zw) <= z_budget) break;
+    }
     z_smem = zstat_smem_bytes<T>(KT, NP, N, zw);
     n_ktiles = (K + KT - 1) / KT;
     const int cts = (int)((G + 31) / 32);
@@ -371,7 +374,7 @@ struct Sampler : bnmf_handle {
     long long need = (items + ZW - 1) / ZW;
     if (bx > need) bx = (int)need;
     dim3 grid(bx, n_ktiles);
-    kern<<<grid, 32 * ZW, z_smem, stream>>>(d, KT, ZR, work_ctr);
+    kern<<<grid, 32 * ZW, z_smem, stream>>>(d, make_zkeys(d.seed), KT, ZR, work_ctr);
     return 0;
   }
   int z_dispatch(bool configure) {

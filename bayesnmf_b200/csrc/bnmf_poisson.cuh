@@ -229,32 +229,44 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
 //
 // Mapping: a warp owns a work item = 32 consecutive genomes (one per lane) x ZR
 // consecutive mutation types and walks down the rows.  Per row:
-//   phase 1 (lane = cell)   the lane builds the running CDF of its cell in a warp-private
-//                           slice of shared memory ([cell][n], odd stride) and the metric
-//                           partials; E[.,g] and the SE accumulators stay in registers.
+//   phase 1 (lane = cell)   the lane accumulates the running CDF of its cell and turns it into
+//                           32-bit integer pick thresholds in a warp-private shared-memory
+//                           table ([n][cell]: bank = cell); metric partials; E[.,g] and the
+//                           SE accumulators stay in registers.
 //   phase 2 (lane = share)  counts per cell are heavy-tailed (max/mean ~ 4 over a warp), so
 //                           the picks of the 32 cells are cut into quads (4 picks = one
 //                           Philox block), laid end to end, and every lane takes an equal
 //                           contiguous share of the row's quads, whatever cells they belong
-//                           to.  A cell that starts inside a lane's share is counted by that
-//                           lane straight into the cell's histogram column (exclusive, no
-//                           atomics); the part of a cell that spills into following lanes
-//                           is counted in those lanes' private columns and folded in by a
-//                           short, conflict-free fix-up (lanes continuing the same cell take
-//                           turns).
+//                           to.  A pick is a branch-free binary search of the cell's threshold
+//                           column (the two top levels sit in registers) that ends on the
+//                           address of its histogram counter.  A cell that starts inside a
+//                           lane's share is counted straight into the cell's histogram column
+//                           (exclusive, no atomics); the part of a cell that spills into
+//                           following lanes is counted in those lanes' private columns and
+//                           folded in by a short, conflict-free fix-up (lanes continuing the
+//                           same cell take turns).
 //   reduce                  REDUX sums the histogram columns across the warp into the
 //                           block-level SP table; each lane adds its own column to SE.
 // SE leaves the SM once per item, SP once per block.  Items are handed out dynamically.
 //
-// Arithmetic contract (what oracle/ restates bit-for-bit):
+// Arithmetic contract (what oracle/ restates bit-for-bit; T = state precision):
 //   p_n   = Pa[k,n] * E[n,g]            (Pa = P with excluded signatures zeroed)
-//   cdf_n = cdf_{n-1} + p_n              (sequential, no FMA)
-//   pick  = min(#{ n : cdf_n <= t }, N-1),  t = (w + 0.5) * (cdf_{N-1} * 2^-32)
-//           [float state: t = ((w >> 8) + 0.5) * (cdf_{N-1} * 2^-24)],
+//   cdf_n = cdf_{n-1} + p_n              (sequential, one rounding per operation, no FMA)
+//   thr_n = sat_u32(floor(cdf_n * (2^32 / cdf_{N-1})))   for n < N-1   (NaN -> 0)
+//   pick  = #{ n < N-1 : thr_n <= min(w, 2^32 - 2) },
 //           w = word (j mod 4) of Philox block j/4 of stream (iter, PUR_Z, k + K*g)
+// i.e. the fp64 inverse CDF evaluated at the 32-bit uniform w: P(pick <= n) = thr_n 2^-32.
 // ------------------------------------------------------------------------------
 // warps per block of k_zstat: 8 up to 32 signatures, 4 beyond (shared memory per warp doubles)
 template <int NP> struct ZWarps { static constexpr int value = NP <= 32 ? 8 : 4; };
+// threshold columns are padded to a power of two (entries >= N-1 hold "never")
+template <int NP> struct ZPad { static constexpr int value = NP <= 4 ? 4 : NP <= 8 ? 8 : NP <= 16 ? 16 : NP <= 32 ? 32 : 64; };
+// rows of a threshold table that a search can touch: NP rounded up to a quarter of the padded width
+__host__ __device__ constexpr int zthr_rows(int NP) {
+  const int NPAD = NP <= 4 ? 4 : NP <= 8 ? 8 : NP <= 16 ? 16 : NP <= 32 ? 32 : 64;
+  const int q = NPAD / 4;
+  return ((NP + q - 1) / q) * q;
+}
 
 template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
 template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
@@ -262,104 +274,137 @@ template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { r
 template <typename T> __device__ __forceinline__ T add_rn(T a, T b);
 template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
 template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+// 2^32 / total, IEEE division
+__device__ __forceinline__ double pick_scale(double total) { return __ddiv_rn(4294967296.0, total); }
+__device__ __forceinline__ float pick_scale(float total) { return __fdiv_rn(4294967296.0f, total); }
+// saturating floor to u32 (NaN -> 0)
+__device__ __forceinline__ uint32_t pick_thr(double x) { return __double2uint_rd(x); }
+__device__ __forceinline__ uint32_t pick_thr(float x) { return __float2uint_rd(x); }
 
-// #{ n < NP : col[n] <= t } for a non-decreasing column whose last entry is > t.
-// Two levels of independent loads (block pivots, then inside the block) instead of a
-// five-deep dependent binary search: the latency of a pick is two shared-memory round trips.
-template <typename T, int NP>
-__device__ __forceinline__ int cdf_search(const T* col, T t) {
-  constexpr int S = NP <= 32 ? 4 : 8;
-  constexpr int NB = NP / S;
-  static_assert(NP % S == 0, "padded signature count must be a multiple of the search block");
-  int b = 0;
+// The ten round keys of Philox4x32-10 for the run seed, computed once on the host: as a kernel
+// parameter they are constant-bank operands of the round's XOR instead of twenty additions per
+// block of random words.
+struct ZKeys { uint32_t k0[10], k1[10]; };
+__host__ inline ZKeys make_zkeys(uint64_t seed) {
+  ZKeys r; uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; ++i) { r.k0[i] = a; r.k1[i] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+  return r;
+}
+__device__ __forceinline__ U4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const ZKeys& rk) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int j = 0; j < NB - 1; ++j) b += (col[(j + 1) * S - 1] <= t) ? 1 : 0;
-  const T* blk = col + b * S;
-  int pos = b * S;
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ rk.k0[r];
+    const uint32_t n2 = hi0 ^ c3 ^ rk.k1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+// The pick loop is issue-bound.  Its shared-memory tables are addressed by 32-bit shared-window
+// addresses (LDS/STS with register + immediate addressing, no 64-bit pointer arithmetic), and a
+// level of the search is a load, a compare and one predicated add.
+extern __shared__ __align__(16) unsigned char smem_raw[];
+template <typename V> __device__ __forceinline__ V* smem_ptr(uint32_t sa) {
+  return reinterpret_cast<V*>(__cvta_shared_to_generic((size_t)sa));
+}
+template <int OFF> __device__ __forceinline__ uint32_t lds_u32_off(uint32_t sa) { return *smem_ptr<const uint32_t>(sa + OFF); }
+// a += INC if v <= w
+template <int INC> __device__ __forceinline__ void add_if_le(uint32_t& a, uint32_t v, uint32_t w) {
+  asm("{ .reg .pred p; setp.le.u32 p, %1, %2; @p add.u32 %0, %0, %3; }" : "+r"(a) : "r"(v), "r"(w), "n"(INC));
+}
+
+// levels S, S/2, .. 1 of four concurrent binary searches (S = remaining half-width in entries)
+template <int S, bool ALL4>
+__device__ __forceinline__ void search_levels(uint32_t (&a)[4], const uint32_t (&ww)[4], int lim) {
+  if constexpr (S >= 1) {
+    uint32_t v[4];
 #pragma unroll
-  for (int j = 0; j < S - 1; ++j) pos += (blk[j] <= t) ? 1 : 0;
-  return pos;
+    for (int p = 0; p < 4; ++p) if (ALL4 || p < lim) v[p] = lds_u32_off<(S - 1) * 128>(a[p]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) if (ALL4 || p < lim) add_if_le<S * 128>(a[p], v[p], ww[p]);
+    search_levels<S / 2, ALL4>(a, ww, lim);
+  }
 }
 
-// Pick threshold t = (w + 0.5) * tots with tots = total * 2^-32 (one rounding each; the same
-// value as u * total, u = (w + 0.5) 2^-32, whenever tots is a normal number).
-// double: 2^52 + w is exact in the mantissa, so w + 0.5 needs no int->double conversion.
-__device__ __forceinline__ double pick_threshold(uint32_t w, double tots) {
-  const double wp = __dadd_rn(__hiloint2double(0x43300000, (int)w), -4503599627370495.5);   // w + 0.5
-  return __dmul_rn(wp, tots);
-}
-// float: 24 random bits, t = ((w >> 8) + 0.5) * (total * 2^-24)
-__device__ __forceinline__ float pick_threshold(uint32_t w, float tots) {
-  return __fmul_rn((float)(w >> 8) + 0.5f, tots);
-}
-template <typename T> __device__ __forceinline__ T pick_scale(T total);
-template <> __device__ __forceinline__ double pick_scale<double>(double total) { return __dmul_rn(total, 2.3283064365386963e-10); }
-template <> __device__ __forceinline__ float pick_scale<float>(float total) { return __fmul_rn(total, 5.9604644775390625e-8f); }
-
-// One quad: four thresholds from one Philox block, four searches, and the histogram update.
-// Equal picks are folded first so that the four read-modify-writes hit distinct addresses and
-// their loads can all be in flight together.  `lim` = picks of the cell still to draw (>= 1);
-// with ALL4 the four searches are straight-line code (no branches) whatever `lim`.
-template <typename T, int NP, bool ALL4>
-__device__ __forceinline__ void zstat_quad(const U4& w, const T* col, T tots, int lim, int N, int* tgt) {
-  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-  int pp[4];
+// One quad: four words of one Philox block, four searches, four counter increments.
+// A search returns the address of thr[#{ n : thr_n <= w }][cell] in the cell's
+// non-decreasing threshold column (row stride 128 bytes, last entry "never"): branch-free binary
+// search, the pivots of its first two levels in registers (loaded once per cell), the four
+// searches advanced level by level so that their loads are in flight together.  `hdb` = byte
+// offset from a threshold entry to the counter of the same (n, cell).  `lim` = picks of the cell
+// still to draw (>= 1); with ALL4 the four searches are straight-line code whatever `lim`.
+template <int NPAD, bool ALL4>
+__device__ __forceinline__ void zstat_quad(const U4& w, uint32_t col, uint32_t tmid, uint32_t tlo, uint32_t thi,
+                                           int lim, uint32_t hdb) {
+  uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  uint32_t a[4];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    pp[p] = 0;
-    if (ALL4 || p < lim) {
-      pp[p] = cdf_search<T, NP>(col, pick_threshold(ww[p], tots));
-      if (sizeof(T) == 4) pp[p] = min(pp[p], N - 1);   // float: t can round up to the total; double: t < total always
+    ww[p] = min(ww[p], 0xfffffffeu);
+    const bool up = tmid <= ww[p];
+    a[p] = up ? col + (NPAD / 2) * 128 : col;
+    add_if_le<(NPAD / 4) * 128>(a[p], up ? thi : tlo, ww[p]);
+  }
+  search_levels<NPAD / 8, ALL4>(a, ww, lim);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p == 0 || p < lim) {
+      int* h = smem_ptr<int>(a[p] + hdb);
+      *h = *h + 1;
     }
   }
-  bool a1 = lim > 1, a2 = lim > 2, a3 = lim > 3;
-  int i0 = 1, i1 = 1, i2 = 1;
-  if (a1 && pp[1] == pp[0]) { i0 += 1; a1 = false; }
-  if (a2 && pp[2] == pp[0]) { i0 += 1; a2 = false; }
-  if (a3 && pp[3] == pp[0]) { i0 += 1; a3 = false; }
-  if (a2 && a1 && pp[2] == pp[1]) { i1 += 1; a2 = false; }
-  if (a3 && a1 && pp[3] == pp[1]) { i1 += 1; a3 = false; }
-  if (a3 && a2 && pp[3] == pp[2]) { i2 += 1; a3 = false; }
-  const int v0 = tgt[pp[0] * 32], v1 = tgt[pp[1] * 32], v2 = tgt[pp[2] * 32], v3 = tgt[pp[3] * 32];
-  tgt[pp[0] * 32] = v0 + i0;
-  if (a1) tgt[pp[1] * 32] = v1 + i1;
-  if (a2) tgt[pp[2] * 32] = v2 + i2;
-  if (a3) tgt[pp[3] * 32] = v3 + 1;
 }
 
-// shared memory of k_zstat in bytes, for a K tile of KT rows (host and device agree on it)
+// shared memory of k_zstat in bytes, for a K tile of KT rows (host and device agree on it):
+// P tile | per warp { thr, hist, cont (int), E tile (T), cell descriptors } | block SP accumulators
+template <typename T> __host__ __device__ inline size_t zstat_warp_bytes(int NP) {
+  return (size_t)32 * (zthr_rows(NP) + 2 * NP) * sizeof(int) + (size_t)32 * NP * sizeof(T) + 136 * sizeof(int);
+}
 template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int KT, int NP, int N, int W) {
-  return (size_t)KT * NP * sizeof(T) + (size_t)W * 32 * (NP + 1) * sizeof(T) + (size_t)W * NP * 32 * 2 * sizeof(int) +
-         (size_t)W * 68 * sizeof(int) + (size_t)KT * N * sizeof(int);
+  return (size_t)KT * NP * sizeof(T) + (size_t)W * zstat_warp_bytes<T>(NP) + (size_t)KT * N * sizeof(int);
 }
 
 template <typename T, int NP>
 __global__ void __launch_bounds__(32 * ZWarps<NP>::value, (NP <= 32 ? 2 : 1))
-k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
+k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ctr) {
   constexpr int W = ZWarps<NP>::value;
   constexpr int ZT = 32 * W;
-  constexpr int NPS = NP + 1;                                        // odd stride: conflict-free columns
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NPAD = ZPad<NP>::value;
+  constexpr int TR = zthr_rows(NP);
   const int K = d.K, N = d.N, G = d.G;
-  T* Psm = reinterpret_cast<T*>(smem_raw);                          // [KT][NP]
-  T* cdf_all = Psm + (size_t)KT * NP;                               // [W][32 cells][NPS]
-  int* hist_all = reinterpret_cast<int*>(cdf_all + (size_t)W * 32 * NPS);  // [W][NP][32 cells]
-  int* cont_all = hist_all + (size_t)W * NP * 32;                   // [W][NP][32 lanes]
-  int* own_all = cont_all + (size_t)W * NP * 32;                    // [W][33 + 32 (+pad)]
-  int* spacc = own_all + (size_t)W * 68;                            // [KT][N]
-  __shared__ int s_item[W];
-
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  T* cdf = cdf_all + (size_t)wid * 32 * NPS;
-  int* hist = hist_all + (size_t)wid * NP * 32;
-  int* cont = cont_all + (size_t)wid * NP * 32;
-  int* s_excl = own_all + wid * 68;              // [33] first quad of each cell (+ total)
-  int* s_m = s_excl + 34;                        // [32] picks of each cell
-  const int ky = blockIdx.y;            // k-tile
+  T* Psm = reinterpret_cast<T*>(smem_raw);                          // [KT][NP]
+  unsigned char* wtabs = reinterpret_cast<unsigned char*>(Psm + (size_t)KT * NP);
+  T* Esm = reinterpret_cast<T*>(wtabs + (size_t)wid * zstat_warp_bytes<T>(NP));   // [NP][32 cells]  E tile of the item
+  uint32_t* thr = reinterpret_cast<uint32_t*>(Esm + NP * 32);       // [TR][32 cells]  pick thresholds of the row
+  int* hist = reinterpret_cast<int*>(thr) + TR * 32;                // [NP][32 cells]  counts of the item so far (its SE)
+  int* cont = hist + NP * 32;                                       // [NP][32 lanes]  counts of a share's spilled first cell
+  int* spacc = reinterpret_cast<int*>(wtabs + (size_t)W * zstat_warp_bytes<T>(NP));   // [KT][N]
+  __shared__ int s_item[W];
+  // cell descriptors of the current row: {first quad, picks, Philox counter words 0,1}; entry 32 = {all quads}
+  int4* desc = reinterpret_cast<int4*>(cont + NP * 32);
+  // shared-window addresses of the two tables; opaque so that they stay in registers instead of
+  // being recomputed inside the (rarely taken, hence sunk-into) cell-switch branch of the pick loop
+  uint32_t thr_sa = (uint32_t)__cvta_generic_to_shared(thr), desc_sa = (uint32_t)__cvta_generic_to_shared(desc);
+  asm volatile("mov.u32 %0, %0;" : "+r"(thr_sa));
+  asm volatile("mov.u32 %0, %0;" : "+r"(desc_sa));
+  const uint32_t c3 = ((uint32_t)d.ctrl->iter << 8) | (uint32_t)PUR_Z;
+#pragma unroll
+  for (int n = 0; n < TR; ++n) thr[n * 32 + lane] = 0xffffffffu;   // entries >= N-1 stay "never"
+#pragma unroll
+  for (int n = 0; n < NP; ++n) { hist[n * 32 + lane] = 0; cont[n * 32 + lane] = 0; }
+
+  // A block starts on K tile blockIdx.y and, when that tile's queue of work items runs dry, moves on
+  // to the next one: mutation types differ widely in their counts, so tiles differ in their work.
+  const int n_ktiles = gridDim.y;
+  for (int tt = 0; tt < n_ktiles; ++tt) {
+  const int ky = (blockIdx.y + tt) % n_ktiles;
   const int k0 = ky * KT;
   const int krows = min(KT, K - k0);
-  const int iter = d.ctrl->iter;
-
   // stage P (with A folded in) and clear block accumulators
   for (int i = tid; i < KT * NP; i += ZT) {
     int kk = i / NP, n = i - kk * NP;
@@ -368,8 +413,6 @@ k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
     Psm[i] = v;
   }
   for (int i = tid; i < KT * N; i += ZT) spacc[i] = 0;
-#pragma unroll
-  for (int n = 0; n < NP; ++n) { hist[n * 32 + lane] = 0; cont[n * 32 + lane] = 0; }
   __syncthreads();
 
   const int rts = (krows + ZR - 1) / ZR;             // row sub-tiles in this k-tile
@@ -389,28 +432,20 @@ k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
     const bool valid = g < G;
     const unsigned long long cell0 = (unsigned long long)K * (unsigned long long)(d.g0 + (long long)ct * 32);
 
-    T Ereg[NP];
-    int se[NP];
-#pragma unroll
-    for (int n = 0; n < NP; ++n) {
-      Ereg[n] = (valid && n < N) ? d.E[(long long)n + (long long)N * g] : (T)0;
-      se[n] = 0;
-    }
+#pragma unroll 4
+    for (int n = 0; n < NP; ++n) Esm[n * 32 + lane] = (valid && n < N) ? d.E[(long long)n + (long long)N * g] : (T)0;
     double a_sse = 0.0, a_kl = 0.0, a_ll = 0.0;
+    int sp_prev0 = 0, sp_prev1 = 0;     // lane n: sum over the tile's cells of hist[n][.] after the previous row
 
     const int kk_end = min(ZR, krows - rt * ZR);
     for (int r = 0; r < kk_end; ++r) {
       const int kk = rt * ZR + r;
       const int k = k0 + kk;
       const int m = valid ? d.Mi[(long long)k + (long long)K * g] : 0;
-      // ---- phase 1: running CDF of this lane's cell ----
-      T acc = (T)0;
+      // ---- phase 1: total of this lane's cell, metric partials ----
+      T total = (T)0;
 #pragma unroll
-      for (int n = 0; n < NP; ++n) {
-        acc = add_rn<T>(acc, mul_rn<T>(Psm[kk * NP + n], Ereg[n]));
-        cdf[lane * NPS + n] = acc;
-      }
-      const T total = acc;
+      for (int n = 0; n < NP; ++n) total = add_rn<T>(total, mul_rn<T>(Psm[kk * NP + n], Esm[n * 32 + lane]));
       if (valid) {
         const double mh = (double)total;
         const double lam = mh > 1e-6 ? mh : 1e-6;
@@ -423,6 +458,18 @@ k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
       }
       const bool work = (m > 0) && (total > (T)0);
       if (!__any_sync(0xffffffffu, work)) continue;
+      // integer pick thresholds of this lane's cell (second pass over the products: reloading the
+      // two tiles is cheaper than 2 NP live registers, which would serialise the pick loop below)
+      {
+        asm volatile("" ::: "memory");
+        const T scale = pick_scale(total);
+        T acc = (T)0;
+#pragma unroll
+        for (int n = 0; n < NP - 1; ++n) {
+          acc = add_rn<T>(acc, mul_rn<T>(Psm[kk * NP + n], Esm[n * 32 + lane]));
+          thr[n * 32 + lane] = n < N - 1 ? pick_thr(mul_rn<T>(acc, scale)) : 0xffffffffu;
+        }
+      }
       // quads of this lane's cell and their offsets in the row's flattened quad list
       const int q = work ? (int)(((unsigned)m + 3u) >> 2) : 0;
       int incl = q;
@@ -433,43 +480,50 @@ k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
       }
       const int excl = incl - q;
       const int Tq = __shfl_sync(0xffffffffu, incl, 31);
-      s_excl[lane] = excl; s_m[lane] = m;
-      if (lane == 31) s_excl[32] = Tq;
-      __syncwarp();   // CDF columns and the cell table visible to the whole warp
+      {
+        const unsigned long long cell = cell0 + (unsigned long long)k + (unsigned long long)((unsigned)K * (unsigned)lane);
+        desc[lane] = make_int4(excl, m, (int)(uint32_t)cell, (int)(uint32_t)(cell >> 32));
+        if (lane == 31) desc[32].x = Tq;
+      }
+      __syncwarp();   // threshold columns and the cell table visible to the whole warp
       // ---- phase 2: an equal contiguous share [qd, qhi) of the row's quads per lane ----
       int qd = (int)(((unsigned long long)lane * (unsigned)Tq) >> 5);
       const int qhi = (int)(((unsigned long long)(lane + 1) * (unsigned)Tq) >> 5);
       // owner of the first quad: the cell c with excl[c] <= qd < excl[c] + q[c]
-      int c = 0, ec = 0;
+      int c_first = 0, ec_first = 0;
 #pragma unroll
       for (int st = 16; st > 0; st >>= 1) {
-        const int e = __shfl_sync(0xffffffffu, excl, c + st);
-        if (e <= qd) { c += st; ec = e; }
+        const int e = __shfl_sync(0xffffffffu, excl, c_first + st);
+        if (e <= qd) { c_first += st; ec_first = e; }
       }
-      int mc = __shfl_sync(0xffffffffu, m, c);
-      const int c_first = c;
-      const bool F = ec < qd;                      // the first cell started in an earlier lane's share
+      const bool F = ec_first < qd;                  // the first cell started in an earlier lane's share
       {
-        int nxt = ec + (int)(((unsigned)mc + 3u) >> 2);
-        const T* col = cdf + c * NPS;
-        int* tgt = F ? cont + lane : hist + c;
-        T tots = pick_scale<T>(col[NP - 1]);
-        unsigned long long cell = cell0 + (unsigned long long)k + (unsigned long long)K * (unsigned)c;
-        const bool dense = Tq >= 96;               // rows of mostly full quads: branch-free searches
+        const bool dense = Tq >= 96;                 // rows of mostly full quads: branch-free searches
+        uint32_t da = desc_sa + 16u * (unsigned)(c_first - 1);
+        int ec = 0, nxt = qd, mc = 0;                // qd >= nxt: the first pass loads the first cell
+        bool spill = F;                              // first cell of a spilled share -> cont[.][lane]
+        uint32_t col = thr_sa, hdb = 0;
+        uint32_t tmid = 0, tlo = 0, thi = 0, cc0 = 0, cc1 = 0;
         for (; qd < qhi; ++qd) {
-          if (qd >= nxt) {          // next cell that has picks; it starts inside this share
-            do { ++c; ec = s_excl[c]; nxt = s_excl[c + 1]; } while (nxt == ec);
-            mc = s_m[c];
-            col = cdf + c * NPS;
-            tgt = hist + c;
-            tots = pick_scale<T>(col[NP - 1]);
-            cell = cell0 + (unsigned long long)k + (unsigned long long)K * (unsigned)c;
+          if (qd >= nxt) {          // next cell that has picks (the first one may have begun earlier)
+            do {
+              da += 16u;
+              const int4 dd = *smem_ptr<const int4>(da);
+              ec = dd.x; mc = dd.y; cc0 = (uint32_t)dd.z; cc1 = (uint32_t)dd.w;
+              nxt = (int)lds_u32_off<16>(da);
+            } while (nxt == ec);
+            const uint32_t c4 = (da - desc_sa) >> 2;           // 4 * cell
+            col = thr_sa + c4;
+            tmid = lds_u32_off<(NPAD / 2 - 1) * 128>(col); tlo = lds_u32_off<(NPAD / 4 - 1) * 128>(col);
+            thi = lds_u32_off<(3 * NPAD / 4 - 1) * 128>(col);
+            hdb = spill ? 4u * (unsigned)((TR + NP) * 32 + lane) - c4 : 4u * TR * 32;   // counter column: cont[.][lane] | hist[.][c]
+            spill = false;
           }
           const int sub = qd - ec;
           const int lim = mc - 4 * sub;              // picks in this quad: min(4, lim) >= 1
-          const U4 w = make_stream(d.seed, iter, PUR_Z, cell).at((uint32_t)sub);
-          if (dense) zstat_quad<T, NP, true>(w, col, tots, lim, N, tgt);
-          else       zstat_quad<T, NP, false>(w, col, tots, lim, N, tgt);
+          const U4 w = philox_rk(cc0, cc1, (uint32_t)sub, c3, rk);
+          if (dense) zstat_quad<NPAD, true>(w, col, tmid, tlo, thi, lim, hdb);
+          else       zstat_quad<NPAD, false>(w, col, tmid, tlo, thi, lim, hdb);
         }
       }
       // ---- fix-up: lanes whose share began inside a cell hand their counts to its column,
@@ -494,25 +548,26 @@ k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
         }
         __syncwarp();
       }
+      // the histogram keeps counting through the rows of the item (its columns are SE); the sum of
+      // a row of it over the tile's cells, minus the same sum one row earlier, is this row's SP
       int mytot0 = 0, mytot1 = 0;
 #pragma unroll
       for (int n = 0; n < NP; ++n) {
-        const int v = hist[n * 32 + lane];
-        hist[n * 32 + lane] = 0;
-        se[n] += v;
-        const int tot = __reduce_add_sync(0xffffffffu, v);
+        const int tot = __reduce_add_sync(0xffffffffu, hist[n * 32 + lane]);
         if (n < 32) { if (lane == n) mytot0 = tot; }
         else        { if (lane == n - 32) mytot1 = tot; }
       }
-      if (lane < N && mytot0) atomicAdd(&spacc[kk * N + lane], mytot0);
-      if (NP > 32 && lane + 32 < N && mytot1) atomicAdd(&spacc[kk * N + lane + 32], mytot1);
-      __syncwarp();   // the CDF columns are rewritten by the next row
+      if (lane < N && mytot0 != sp_prev0) atomicAdd(&spacc[kk * N + lane], mytot0 - sp_prev0);
+      if (NP > 32 && lane + 32 < N && mytot1 != sp_prev1) atomicAdd(&spacc[kk * N + lane + 32], mytot1 - sp_prev1);
+      sp_prev0 = mytot0; sp_prev1 = mytot1;
+      __syncwarp();   // the threshold columns are rewritten by the next row
     }
     // SE leaves the SM once per item
-    if (valid) {
 #pragma unroll
-      for (int n = 0; n < NP; ++n)
-        if (n < N && se[n]) atomicAdd(&d.SE[(long long)n + (long long)N * g], se[n]);
+    for (int n = 0; n < NP; ++n) {
+      const int v = hist[n * 32 + lane];
+      hist[n * 32 + lane] = 0;
+      if (valid && n < N && v) atomicAdd(&d.SE[(long long)n + (long long)N * g], v);
     }
     // per-item metric partials, fixed reduction order
     a_sse = warp_sum(a_sse); a_kl = warp_sum(a_kl); a_ll = warp_sum(a_ll);
@@ -529,6 +584,8 @@ k_zstat(Dev<T> d, int KT, int ZR, int* work_ctr) {
       const int kk = i / N, n = i - kk * N;
       atomicAdd(&d.SP[(long long)(k0 + kk) + (long long)K * n], (unsigned long long)v);
     }
+  }
+  __syncthreads();   // the P tile and the accumulators are rewritten for the next K tile
   }
 }
 

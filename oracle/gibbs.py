@@ -102,19 +102,36 @@ def z_cdf(P, A, E, f32=False):
     return np.add.accumulate(prob, axis=1, dtype=dt)                # sequential adds, no pairwise
 
 
+def z_thresholds(cdf, N, f32=False):
+    """32-bit integer pick thresholds of every cell: thr_n = sat_u32(floor(cdf_n * (2^32 / cdf_{N-1})))
+    for n < N-1 (NaN -> 0, as the float -> unsigned conversion of the kernel does), evaluated in
+    the state precision with one rounding per operation.  P(pick <= n) = thr_n * 2^-32."""
+    dt = np.float32 if f32 else np.float64
+    total = cdf[:, -1, :]
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        scale = dt(4294967296.0) / total                       # IEEE division
+        x = (cdf[:, : N - 1, :] * scale[:, None, :]).astype(dt)
+    x = np.where(np.isnan(x), 0.0, x)
+    return np.clip(np.floor(x).astype(np.float64), 0.0, 4294967295.0).astype(np.uint64)   # K x (N-1) x G
+
+
 def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_000_000, f32=False):
     """sample_Zkg for every cell, reduced to SP = sum_g Z (K x N), SE = sum_k Z (N x G).
 
     Reference: probs_n = P[k,n]*A[1,n]*E[n,g]; all-zero -> Z = 0; else
     rmultinom(1, size = M[k,g], prob = probs/sum(probs))  (R/sample_params.R:253-265).
     rmultinom is a chain of conditional binomials; a multinomial is equally the
-    histogram of M[k,g] independent categorical draws, which is what is used here
-    (fp64 inverse CDF; pick = #{n : cdf_n <= u * cdf_N}, u = (w + 0.5) 2^-32)."""
+    histogram of M[k,g] independent categorical draws, which is what is used here: the
+    inverse of the running CDF (accumulated in the state precision) at the 32-bit uniform
+    w of the pick, pick = #{n < N-1 : thr_n <= min(w, 2^32 - 2)} with the integer thresholds
+    of z_thresholds (the arithmetic contract of k_zstat, csrc/bnmf_poisson.cuh).
+    `bits` is accepted for symmetry with the draw functions and not used."""
     M = np.asarray(M)
     K, G = M.shape
     N = P.shape[1]
     cdf = z_cdf(P, A, E, f32)                      # K x N x G
     total = cdf[:, -1, :]                          # K x G  == Mhat
+    thr = z_thresholds(cdf, N, f32)                # K x (N-1) x G
     Mi = M.astype(np.int64)
     work = (Mi > 0) & (total > 0.0)
     kk, gg = np.nonzero(work)
@@ -138,19 +155,10 @@ def sample_Z_stats(M, P, A, E, seed, it, g0=0, bits=32, return_Z=False, chunk=2_
         j = np.arange(len(owner)) - np.repeat(starts[c0:c1] - starts[c0], cs)
         w = px.words(seed, it, px.PUR_Z, cell_id[owner], j >> 2)
         W = np.stack(w, axis=0)
-        word = W[j & 3, np.arange(len(owner))]
-        # t = (w + 0.5) * (total * 2^-32): the same number as u01(w) * total (power-of-two
-        # scaling is exact), written the way the kernel evaluates it
-        if f32:     # float state: 24 random bits, float32 arithmetic throughout
-            tots = total[kk[owner], gg[owner]] * np.float32(2.0 ** -24)
-            t = ((word >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * tots
-        elif bits == 32:
-            t = (word.astype(np.float64) + 0.5) * (total[kk[owner], gg[owner]] * 2.0 ** -32)
-        else:
-            t = ((word >> np.uint32(8)).astype(np.float64) + 0.5) * (total[kk[owner], gg[owner]] * 2.0 ** -24)
-        cd = cdf[kk[owner], :, gg[owner]]          # picks x N
-        pick = (cd <= t[:, None]).sum(axis=1)
-        pick = np.minimum(pick, N - 1)
+        word = W[j & 3, np.arange(len(owner))].astype(np.uint64)
+        word = np.minimum(word, np.uint64(0xFFFFFFFE))
+        th = thr[kk[owner], :, gg[owner]]          # picks x (N-1)
+        pick = (th <= word[:, None]).sum(axis=1)
         np.add.at(SP, (kk[owner], pick), 1)
         np.add.at(SE, (pick, gg[owner]), 1)
         if return_Z:
