@@ -337,19 +337,24 @@ __device__ __forceinline__ void search_levels(uint32_t (&a)[4], const uint32_t (
 // searches advanced level by level so that their loads are in flight together.  `hdb` = byte
 // offset from a threshold entry to the counter of the same (n, cell).  `lim` = picks of the cell
 // still to draw (>= 1); with ALL4 the four searches are straight-line code whatever `lim`.
+struct ZPivots { uint32_t mid, lo, hi, q0, q1, q2, q3; };   // entries NPAD/2-1 | NPAD/4-1, 3NPAD/4-1 | (2j+1)NPAD/8-1
 template <int NPAD, bool ALL4>
-__device__ __forceinline__ void zstat_quad(const U4& w, uint32_t col, uint32_t tmid, uint32_t tlo, uint32_t thi,
-                                           int lim, uint32_t hdb) {
+__device__ __forceinline__ void zstat_quad(const U4& w, uint32_t col, const ZPivots& pv, int lim, uint32_t hdb) {
   uint32_t ww[4] = {w.x, w.y, w.z, w.w};
   uint32_t a[4];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     ww[p] = min(ww[p], 0xfffffffeu);
-    const bool up = tmid <= ww[p];
+    const bool up = pv.mid <= ww[p];
     a[p] = up ? col + (NPAD / 2) * 128 : col;
-    add_if_le<(NPAD / 4) * 128>(a[p], up ? thi : tlo, ww[p]);
+    const bool up2 = (up ? pv.hi : pv.lo) <= ww[p];
+    if (up2) a[p] += (NPAD / 4) * 128;
+    if (NPAD >= 8) {
+      const uint32_t lo3 = up ? pv.q2 : pv.q0, hi3 = up ? pv.q3 : pv.q1;
+      add_if_le<(NPAD / 8) * 128>(a[p], up2 ? hi3 : lo3, ww[p]);
+    }
   }
-  search_levels<NPAD / 8, ALL4>(a, ww, lim);
+  search_levels<NPAD / 16, ALL4>(a, ww, lim);
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     if (p == 0 || p < lim) {
@@ -503,7 +508,8 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ct
         int ec = 0, nxt = qd, mc = 0;                // qd >= nxt: the first pass loads the first cell
         bool spill = F;                              // first cell of a spilled share -> cont[.][lane]
         uint32_t col = thr_sa, hdb = 0;
-        uint32_t tmid = 0, tlo = 0, thi = 0, cc0 = 0, cc1 = 0;
+        ZPivots pv = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        uint32_t cc0 = 0, cc1 = 0;
         for (; qd < qhi; ++qd) {
           if (qd >= nxt) {          // next cell that has picks (the first one may have begun earlier)
             do {
@@ -514,39 +520,50 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ct
             } while (nxt == ec);
             const uint32_t c4 = (da - desc_sa) >> 2;           // 4 * cell
             col = thr_sa + c4;
-            tmid = lds_u32_off<(NPAD / 2 - 1) * 128>(col); tlo = lds_u32_off<(NPAD / 4 - 1) * 128>(col);
-            thi = lds_u32_off<(3 * NPAD / 4 - 1) * 128>(col);
+            // pivots of the first three levels of the search (rows >= TR do not exist: "never")
+            pv.mid = lds_u32_off<(NPAD / 2 - 1) * 128>(col);
+            pv.lo = lds_u32_off<(NPAD / 4 - 1) * 128>(col); pv.hi = lds_u32_off<(3 * NPAD / 4 - 1) * 128>(col);
+            if (NPAD >= 8) {
+              pv.q0 = lds_u32_off<(NPAD / 8 - 1) * 128>(col);
+              pv.q1 = lds_u32_off<(3 * NPAD / 8 - 1) * 128>(col);
+              pv.q2 = (5 * NPAD / 8 - 1 < TR) ? lds_u32_off<(5 * NPAD / 8 - 1) * 128>(col) : 0xffffffffu;
+              pv.q3 = (7 * NPAD / 8 - 1 < TR) ? lds_u32_off<(7 * NPAD / 8 - 1) * 128>(col) : 0xffffffffu;
+            }
             hdb = spill ? 4u * (unsigned)((TR + NP) * 32 + lane) - c4 : 4u * TR * 32;   // counter column: cont[.][lane] | hist[.][c]
             spill = false;
           }
           const int sub = qd - ec;
           const int lim = mc - 4 * sub;              // picks in this quad: min(4, lim) >= 1
           const U4 w = philox_rk(cc0, cc1, (uint32_t)sub, c3, rk);
-          if (dense) zstat_quad<NPAD, true>(w, col, tmid, tlo, thi, lim, hdb);
-          else       zstat_quad<NPAD, false>(w, col, tmid, tlo, thi, lim, hdb);
+          if (dense) zstat_quad<NPAD, true>(w, col, pv, lim, hdb);
+          else       zstat_quad<NPAD, false>(w, col, pv, lim, hdb);
         }
       }
-      // ---- fix-up: lanes whose share began inside a cell hand their counts to its column,
-      //      one lane per cell at a time (lanes continuing the same cell are consecutive) ----
+      // ---- fix-up: lanes whose share began inside a cell hand their counts to its column.  Lanes
+      //      continuing the same cell are consecutive: their columns are first summed into the
+      //      first of them by a segmented shuffle reduction, so one pass serves every cell ----
       {
         const unsigned fm = __ballot_sync(0xffffffffu, F);
-        const int cprev = __shfl_up_sync(0xffffffffu, c_first, 1);
-        const bool chain = F && lane > 0 && ((fm >> (lane - 1)) & 1u) && cprev == c_first;
-        const unsigned bm = __ballot_sync(0xffffffffu, chain);
-        const unsigned x = ~bm & (0xffffffffu >> (31 - lane));     // lanes <= me that do not chain (lane 0 never does)
-        const int turn = F ? 1 + lane - (31 - __clz(x)) : 0;
-        const int turns = __reduce_max_sync(0xffffffffu, turn);
-        for (int j = 1; j <= turns; ++j) {
-          __syncwarp();
-          if (turn == j) {
+        if (fm) {
+          const int cprev = __shfl_up_sync(0xffffffffu, c_first, 1);
+          const bool chain = F && lane > 0 && ((fm >> (lane - 1)) & 1u) && cprev == c_first;
+          const unsigned bm = __ballot_sync(0xffffffffu, chain);
+          const unsigned above = lane < 31 ? (bm >> (lane + 1)) : 0u;
+          const int run = F ? __ffs((int)~above) - 1 : 0;          // lanes lane+1 .. lane+run continue my first cell
+          const int maxrun = __reduce_max_sync(0xffffffffu, run);
+          const bool head = F && !chain;
 #pragma unroll
-            for (int n = 0; n < NP; ++n) {
-              const int v = cont[n * 32 + lane];
-              if (v) { hist[n * 32 + c_first] += v; cont[n * 32 + lane] = 0; }
+          for (int n = 0; n < NP; ++n) {
+            int v = cont[n * 32 + lane];
+            if (F) cont[n * 32 + lane] = 0;
+            for (int dd = 1; dd <= maxrun; dd <<= 1) {
+              const int t = __shfl_down_sync(0xffffffffu, v, dd);
+              if (dd <= run) v += t;
             }
+            if (head && v) hist[n * 32 + c_first] += v;
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       // the histogram keeps counting through the rows of the item (its columns are SE); the sum of
       // a row of it over the tile's cells, minus the same sum one row earlier, is this row's SP
