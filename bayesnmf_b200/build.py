@@ -13,7 +13,7 @@ SRC = os.path.join(HERE, "csrc", "bnmf_api.cu")
 OUT = os.path.join(HERE, "libbnmf_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false", "-Xcompiler", "-fPIC", "-shared",
+    "-fmad=false", "-Xcompiler", "-fPIC,-pthread", "-shared",
 ]
 
 

@@ -6,10 +6,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bnmf.h"
@@ -150,6 +154,11 @@ struct Sampler : bnmf_handle {
   Dev<T> d;
   cudaStream_t stream = nullptr;
   std::vector<void*> allocs;
+  // device arrays below 64 MiB are carved out of 64 MiB slabs (zero-filled once): a handle owns
+  // ~40 arrays, and cudaMalloc costs up to a millisecond apiece when the device is in use
+  struct Slab { char* base; size_t cap, used; };
+  std::vector<Slab> slabs;
+  static constexpr size_t SLAB_BYTES = (size_t)64 << 20;
   std::map<std::string, StEntry> st;
   std::map<std::string, Hyper<T>*> hy;
   std::map<std::string, long long> hy_len;
@@ -186,9 +195,22 @@ struct Sampler : bnmf_handle {
 
   template <typename X> int dalloc(X** p, long long n) {
     if (n < 1) n = 1;
-    CK(cudaMalloc((void**)p, (size_t)n * sizeof(X)));
-    CK(cudaMemsetAsync(*p, 0, (size_t)n * sizeof(X), stream));
-    allocs.push_back(*p);
+    const size_t bytes = (((size_t)n * sizeof(X)) + 255) & ~(size_t)255;
+    if (bytes >= SLAB_BYTES) {
+      CK(cudaMalloc((void**)p, bytes));
+      CK(cudaMemsetAsync(*p, 0, bytes, stream));
+      allocs.push_back(*p);
+      return 0;
+    }
+    if (slabs.empty() || slabs.back().used + bytes > slabs.back().cap) {
+      char* base;
+      CK(cudaMalloc((void**)&base, SLAB_BYTES));
+      CK(cudaMemsetAsync(base, 0, SLAB_BYTES, stream));
+      allocs.push_back(base);
+      slabs.push_back(Slab{base, SLAB_BYTES, 0});
+    }
+    *p = reinterpret_cast<X*>(slabs.back().base + slabs.back().used);
+    slabs.back().used += bytes;
     return 0;
   }
   int reg(const char* name, T** p, long long n) {
@@ -207,6 +229,14 @@ struct Sampler : bnmf_handle {
   static int blocks(long long n, int t) { return (int)((n + t - 1) / t); }
 
   int create(const bnmf_config* c, const double* data) {
+    const bool trace = getenv("BNMF_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!trace) return;
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[bnmf_create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    };
     cfg = *c;
     if (cfg.K < 1 || cfg.N < 1 || cfg.G < 1) return fail("bnmf_create: K, N, G must be >= 1");
     if (cfg.N > 64) return fail("bnmf_create: N = %d > 64 is not supported by this build", cfg.N);
@@ -214,6 +244,7 @@ struct Sampler : bnmf_handle {
     CK(cudaSetDevice(cfg.device));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    lap("stream + events");
     memset(&d, 0, sizeof(d));
     const int K = cfg.K, N = cfg.N; const long long G = cfg.G;
     d.K = K; d.N = N; d.G = (int)G; d.G_total = cfg.G_total; d.g0 = cfg.g0;
@@ -286,28 +317,68 @@ struct Sampler : bnmf_handle {
       if (dalloc(&d.ring_P, (long long)d.ring_cap * KN) || dalloc(&d.ring_E, (long long)d.ring_cap * NG) ||
           dalloc(&d.ring_A, (long long)d.ring_cap * N)) return 1;
     }
-    // data
-    if (ensure_stage(KG)) return 1;
-    CK(cudaMemcpyAsync(stage, data, (size_t)KG * sizeof(double), cudaMemcpyHostToDevice, stream));
-    if (cfg.likelihood == BNMF_POISSON) {
-      // counts: non-negative integers; a cell below 2^24 and a genome (column) total below 2^31
-      // keep the quad offsets of k_zstat and the int32 margins SE exact
-      for (long long g = 0; g < G; ++g) {
-        double colsum = 0.0;
-        for (int k = 0; k < K; ++k) {
-          const long long i = k + (long long)K * g;
-          const double v = data[i];
-          if (!(v >= 0.0) || v != std::floor(v))
-            return fail("bnmf_create: Poisson likelihood needs non-negative integer counts (data[%lld] = %g)", i, v);
-          if (v > 16777216.0)
-            return fail("bnmf_create: count %g at data[%lld] exceeds the supported 2^24 per cell", v, i);
-          colsum += v;
+    lap("allocations");
+    // data: one threaded pass over the caller's matrix (validation, column totals, the sum for
+    // mean(data), conversion of counts to int32) in fixed chunks of columns, so that the result
+    // does not depend on the number of threads
+    const long long CH = 1024;                                   // columns per chunk
+    const long long n_ch = (G + CH - 1) / CH;
+    std::vector<long double> ch_sum((size_t)n_ch, 0.0L);
+    std::vector<long long> ch_bad((size_t)n_ch, -1);             // first offending cell of a chunk
+    std::vector<int> ch_why((size_t)n_ch, 0);
+    std::vector<int32_t> h_mi;
+    const bool pois = cfg.likelihood == BNMF_POISSON;
+    if (pois) h_mi.resize((size_t)KG);
+    {
+      auto work = [&](long long c) {
+        const long long g_lo = c * CH, g_hi = std::min(G, g_lo + CH);
+        long double sum = 0.0L;
+        for (long long g = g_lo; g < g_hi; ++g) {
+          double colsum = 0.0;
+          for (int k = 0; k < K; ++k) {
+            const long long i = k + (long long)K * g;
+            const double v = data[i];
+            if (pois) {
+              // counts: non-negative integers; a cell up to 2^24 and a genome (column) total below
+              // 2^31 keep the quad offsets of k_zstat and the int32 margins SE exact
+              if (!(v >= 0.0) || v != std::floor(v)) { if (ch_bad[c] < 0) { ch_bad[c] = i; ch_why[c] = 1; } continue; }
+              if (v > 16777216.0) { if (ch_bad[c] < 0) { ch_bad[c] = i; ch_why[c] = 2; } continue; }
+              h_mi[(size_t)i] = (int32_t)v;
+            }
+            colsum += v;
+          }
+          if (pois && colsum >= 2147483648.0 && ch_bad[c] < 0) { ch_bad[c] = g; ch_why[c] = 3; }
+          sum += (long double)colsum;
         }
-        if (colsum >= 2147483648.0)
-          return fail("bnmf_create: column %lld sums to %g counts, the supported maximum is 2^31 - 1", g, colsum);
-      }
+        ch_sum[(size_t)c] = sum;
+      };
+      unsigned nt = std::thread::hardware_concurrency();
+      if (nt < 1) nt = 1;
+      if (nt > 16) nt = 16;
+      if ((long long)nt > n_ch) nt = (unsigned)n_ch;
+      if (KG < (1 << 20)) nt = 1;
+      std::atomic<long long> next(0);
+      auto loop = [&]() { for (long long c; (c = next.fetch_add(1)) < n_ch;) work(c); };
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < nt; ++t) th.emplace_back(loop);
+      loop();
+      for (auto& t : th) t.join();
+    }
+    for (long long c = 0; c < n_ch; ++c) {
+      if (ch_bad[c] < 0) continue;
+      const long long i = ch_bad[c];
+      if (ch_why[c] == 1) return fail("bnmf_create: Poisson likelihood needs non-negative integer counts (data[%lld] = %g)", i, data[i]);
+      if (ch_why[c] == 2) return fail("bnmf_create: count %g at data[%lld] exceeds the supported 2^24 per cell", data[i], i);
+      return fail("bnmf_create: column %lld sums to 2^31 counts or more, the supported maximum is 2^31 - 1", i);
+    }
+    long double data_sum = 0.0L;
+    for (long long c = 0; c < n_ch; ++c) data_sum += ch_sum[(size_t)c];
+    lap("host pass over data");
+    if (pois) {
       int32_t* mi; if (dalloc(&mi, KG)) return 1;
-      k_cvt_in_i32<<<blocks(KG, 256), 256, 0, stream>>>(stage, mi, KG);
+      lap("alloc counts");
+      CK(cudaMemcpyAsync(mi, h_mi.data(), (size_t)KG * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+      lap("memcpy counts");
       d.Mi = mi;
       const int nb = 296;
       double* cpart; if (dalloc(&cpart, 2 * nb)) return 1;
@@ -319,6 +390,8 @@ struct Sampler : bnmf_handle {
       for (int i = 0; i < nb; ++i) { a += hc[2 * i]; b += hc[2 * i + 1]; }
       d.ll_const = a; d.kl_const = b;
     } else {
+      if (ensure_stage(KG)) return 1;
+      CK(cudaMemcpyAsync(stage, data, (size_t)KG * sizeof(double), cudaMemcpyHostToDevice, stream));
       T* mr; if (dalloc(&mr, KG)) return 1;
       k_cvt_in<T><<<blocks(KG, 256), 256, 0, stream>>>(stage, mr, KG);
       d.Mr = mr;
@@ -333,17 +406,17 @@ struct Sampler : bnmf_handle {
       for (int i = 0; i < nb; ++i) b += hc[2 * i + 1];
       d.ll_const = 0.0; d.kl_const = b;
     }
+    lap("upload + data constants");
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (z_config()) return 1; }
     if (mh_setup()) return 1;
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
+    lap("kernel attributes, sweep setup");
     // default hyperprior parameters (get_default_*_hyperprior_params_, R/setup.R:123-181);
     // bnmf_set_hyper overrides them.  mean(data) is over this handle's columns: sharded runs
     // pass the global defaults explicitly.
     {
-      long double sum = 0.0L;
-      for (long long i = 0; i < KG; ++i) sum += data[i];
-      const double mean = (double)(sum / (long double)KG), dN = (double)N;
+      const double mean = (double)(data_sum / (long double)KG), dN = (double)N;
       struct DV { const char* n; double v; };
       std::vector<DV> dv;
       if (cfg.prior == BNMF_TRUNCNORMAL) dv = {{"M", 0.0}, {"S", std::sqrt(mean / dN)}, {"A", dN + 1.0}, {"B", std::sqrt(dN)}};

@@ -127,7 +127,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = dict(WORKLOADS[args.workload])
     K, G, N = w["K"], w["G"], w["N"]
-    M = synth(w)
+    # the host buffer in the reference's own layout: R matrices are column-major doubles (REALSXP)
+    M = np.asfortranarray(synth(w), dtype=np.float64)
     g_lo, g_hi = shard_bounds(G, rank, world)
     prec = args.precision
     elem = 8 if prec == "f64" else 4
@@ -193,11 +194,14 @@ def run_b200(args):
     sync()
     e0 = time.time()
     h2 = make(share_comm=h if world > 1 else None)
+    ea = time.time()
     h2.init_from_prior()
     o2 = h2.step(args.steps, want_P=True, want_A=True)
+    eb = time.time()
     E_last = h2.get_state("E")
     torch.cuda.synchronize()
     e1 = time.time()
+    print(f"[e2e rank {rank}] construct+upload {ea - e0:.3f}s, prior draw + {args.steps} steps {eb - ea:.3f}s, final E {e1 - eb:.3f}s", file=sys.stderr)
     h2.close()
     h.close()
     e2e_s = e1 - e0
