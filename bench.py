@@ -85,7 +85,10 @@ class ClockSampler:
     def __exit__(self, *a):
         if self.proc:
             time.sleep(0.15)
-            self.proc.terminate()
+            # gone before anything else is timed: a polling nvidia-smi holds the driver's lock for
+            # milliseconds at a time, which shows up in every cudaMalloc / cudaMemcpy of this process
+            self.proc.kill()
+            self.proc.wait()
             self.th.join(timeout=2)
 
     def summary(self, t0, t1):
