@@ -54,6 +54,15 @@ def ncu_traffic(kernel, workload, prec, world):
     return None if e is None else e["bytes_per_launch"]
 
 
+def ncu_limiters(kernel, workload, prec, world):
+    """What the committed ncu capture says bounds `kernel` (issue slots, shared-memory pipe, DRAM)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(f"{kernel}:{workload}:{prec}")
+    return None if e is None else e.get("limiters")
+
+
 def z_algorithmic_bytes(K, G, N, elem):
     """Bytes the fused latent-count kernel must move per launch: M read once (int32),
     E read once and SE written once, P read and SP written once."""
@@ -239,6 +248,7 @@ def run_b200(args):
                      "frac": achieved / peak, "traffic": ncu_traffic("k_zstat", args.workload, prec, world), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": zb, "avg_launch_ms": z_avg_ms,
                      "share_of_step": z_ms / iter_ms if iter_ms else None,
+                     "limiters_ncu": ncu_limiters("k_zstat", args.workload, prec, world),
                      "latent_picks_per_s": float(M[:, g_lo:g_hi].sum()) / (z_avg_ms * 1e-3) if z_avg_ms > 0 else None},
         "last_metrics": {"RMSE": float(last_row[1]), "loglikelihood": float(last_row[3])},
     }
