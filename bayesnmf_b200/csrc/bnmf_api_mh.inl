@@ -43,6 +43,61 @@ template <typename T> int Sampler<T>::mh_setup() {
   e_wpb = (int)std::min<long long>(8, w);
   e_smem = (size_t)(1 + 2 * e_wpb) * K * sizeof(double);
   CK(cudaFuncSetAttribute(k_e_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
+  // Row-resident P sweep: a cluster of CS blocks per mutation type keeps the row of M and Mhat in
+  // shared memory.  CS is the cluster size that needs the fewest waves of clusters over the K rows
+  // (ties: the smaller slice per block); BNMF_P_ROWS=0 keeps the pass-per-signature kernels.
+  const char* pr_env = getenv("BNMF_P_ROWS");
+  if (sweep_model && !(pr_env && atoi(pr_env) == 0)) {
+    const bool normal = cfg.likelihood == BNMF_NORMAL;
+    const long long EA = 16 / (long long)sizeof(T);
+    pr_Gp = ((G + EA - 1) / EA) * EA;
+    double best = 0.0;
+    for (int cs = 1; cs <= 8; ++cs) {
+      long long gs = (G + cs - 1) / cs;
+      gs = ((gs + EA - 1) / EA) * EA;
+      const int threads = gs >= 2048 ? 512 : 256;
+      const size_t smem = p_rows_smem<T>((int)gs, threads, normal);
+      if (smem > (size_t)220 * 1024) continue;
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3((unsigned)(cs * K)); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = smem; lc.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      int nclusters = 0;
+      cudaError_t e1, e2;
+      if (threads == 512) {
+        e1 = cudaFuncSetAttribute(k_p_rows<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e2 = cudaOccupancyMaxActiveClusters(&nclusters, k_p_rows<T, 512>, &lc);
+      } else {
+        e1 = cudaFuncSetAttribute(k_p_rows<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e2 = cudaOccupancyMaxActiveClusters(&nclusters, k_p_rows<T, 256>, &lc);
+      }
+      if (e1 != cudaSuccess || e2 != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+      const long long waves = (K + nclusters - 1) / nclusters;
+      const double cost = (double)waves * (1.0 + (double)gs / 16384.0);   // fixed latency per signature + the slice
+      if (getenv("BNMF_TRACE")) fprintf(stderr, "[k_p_rows] cs %d slice %lld threads %d smem %zu clusters %d waves %lld cost %.2f\n", cs, gs, threads, smem, nclusters, waves, cost);
+      if (pr_cs == 0 || cost < best) { best = cost; pr_cs = cs; pr_gslice = (int)gs; pr_threads = threads; pr_smem = smem; }
+    }
+    if (pr_cs) {
+      if (pr_threads == 512) CK(cudaFuncSetAttribute(k_p_rows<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr_smem));
+      else CK(cudaFuncSetAttribute(k_p_rows<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr_smem));
+      if (dalloc(&Et, (long long)N * pr_Gp)) return 1;
+    }
+  }
+  return 0;
+}
+
+template <typename T> int Sampler<T>::p_rows_launch() {
+  const long long NG = (long long)cfg.N * cfg.G;
+  k_transpose_E<T><<<blocks(NG, 256), 256, 0, stream>>>(d, Et, pr_Gp); ++launches;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)(pr_cs * cfg.K)); lc.blockDim = dim3(pr_threads); lc.dynamicSmemBytes = pr_smem; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = pr_cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  if (pr_threads == 512) CK(cudaLaunchKernelEx(&lc, k_p_rows<T, 512>, d, (const T*)Et, pr_Gp, pr_cs, pr_gslice));
+  else CK(cudaLaunchKernelEx(&lc, k_p_rows<T, 256>, d, (const T*)Et, pr_Gp, pr_cs, pr_gslice));
+  ++launches;
   return 0;
 }
 
@@ -92,7 +147,8 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
     const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
     const size_t psm = (size_t)p_kx * p_gy * 2 * sizeof(double);
     const int dblocks = (K + 3) / 4;       // k_p_draw / k_p_accept: a warp per mutation type
-    for (int n = 0; n < N; ++n) {
+    if (pr_cs) { if (p_rows_launch()) return 1; }
+    else for (int n = 0; n < N; ++n) {
       k_p_pass1<T><<<pgrid, pblock, psm, stream>>>(d, n, n ? n - 1 : -1);
       k_p_draw<T><<<dblocks, 128, 0, stream>>>(d, n);
       launches += 2;
@@ -102,7 +158,7 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
         launches += 2;
       }
     }
-    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, N - 1); ++launches;
+    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, pr_cs ? -1 : N - 1); ++launches;
     int pending = -1;
     if (cfg.learning_rank) { if (rank_sweep_kernels(&pending)) return 1; }
     k_final<T><<<col_blocks, 256, 0, stream>>>(d, pending, 0); ++launches;

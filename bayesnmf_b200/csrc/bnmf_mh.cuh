@@ -325,6 +325,278 @@ __global__ void k_p_accept(Dev<T> d, int n) {
 }
 
 // ------------------------------------------------------------------------------
+// k_p_rows: the whole P sweep in one launch.  The conditionals of P[k, .] touch only row k of
+// M and of the running Mhat, so a thread-block cluster owns one mutation type: its CS blocks
+// keep disjoint slices of the row in shared memory for all N signatures (M and Mhat are read
+// once per iteration instead of once or twice per signature).  Row n of E -- read from a
+// transposed copy made once per iteration, genomes contiguous -- arrives by a bulk asynchronous
+// copy (cp.async.bulk + mbarrier) into one of two buffers while signature n-1 is being drawn.
+// The sums over genomes are reduced inside the block and then across the cluster through
+// distributed shared memory; block 0 draws (and, after convergence, runs the Metropolis-Hastings
+// accept step on a second cluster-wide sum) and hands the change of P[k,n] back to every
+// block, which applies the rank-1 correction to its slice.
+// Same arithmetic as k_p_pass1 / k_p_draw / k_p_pass2 / k_p_accept, a different (fixed)
+// summation order.
+// ------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_transpose_E(Dev<T> d, T* __restrict__ Et, long long Gp) {
+  // Et[n * Gp + g] = E[n + N * g]   (row stride Gp = G rounded up to an even number of elements)
+  const long long NG = (long long)d.N * d.G;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NG) return;
+  const long long n = i / d.G, g = i - n * d.G;
+  Et[n * Gp + g] = d.E[n + (long long)d.N * g];
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the shared memory of block `rank` of this cluster (same offset as `local`)
+__device__ __forceinline__ void dsmem_store(double* local, uint32_t rank, double v) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(sa), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(ra), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tBNMF_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra BNMF_DONE;\n\tbra BNMF_WAIT;\n\tBNMF_DONE:\n\t}"
+      :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// bulk asynchronous copy global -> shared memory of this block; bytes, src and dst multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// sum of (a, b) over the block in a fixed order; valid in thread 0
+template <int THREADS>
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch /*2 * THREADS/32*/) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { scratch[2 * wid] = a; scratch[2 * wid + 1] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0.0; b = 0.0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) { a += scratch[2 * w]; b += scratch[2 * w + 1]; }
+  }
+}
+
+// attempts of every truncated-normal draw of a row whose base variates are computed up front, in parallel
+constexpr int P_PRE = 4;
+// bytes of shared memory of k_p_rows for a slice of gslice genomes (gslice a multiple of 16 / sizeof(T))
+template <typename T> __host__ __device__ inline size_t p_rows_smem(int gslice, int threads, bool normal) {
+  return (size_t)gslice * (3 * sizeof(T) + (normal ? sizeof(T) + sizeof(double) : sizeof(int32_t))) + 16 +
+         (size_t)(2 * (threads / 32) + 18 + 3 * 64 + 3 * 64 * P_PRE) * sizeof(double) + 2 * sizeof(uint64_t) + 2 * 64 * sizeof(int);
+}
+
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_p_rows(Dev<T> d, const T* __restrict__ Et, long long Gp, int CS, int gslice) {
+  extern __shared__ __align__(16) unsigned char prow_raw[];
+  const int K = d.K, N = d.N, G = d.G;
+  const int tid = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const int k = blockIdx.x / CS;
+  const int g0 = (int)rank * gslice;
+  const int ng = max(0, min(G, g0 + gslice) - g0);
+  constexpr int EA = 16 / (int)sizeof(T);                                    // elements per 16 bytes: bulk copies move whole 16-byte units
+  const uint32_t e_bytes = (uint32_t)(((ng + EA - 1) / EA) * 16);
+  const bool normal = d.likelihood == LIK_NORMAL;
+  // shared: E buffers (2 x T) | Mhat slice (T) | M slice (T or int32) | reduction scratch | mailbox | broadcast slot | 2 mbarriers
+  T* Eb0 = smem_ptr<T>((uint32_t)__cvta_generic_to_shared(prow_raw));
+  T* Mh = smem_ptr<T>((uint32_t)__cvta_generic_to_shared(prow_raw) + 2u * (uint32_t)gslice * (uint32_t)sizeof(T));
+  unsigned char* after = reinterpret_cast<unsigned char*>(Mh + gslice);
+  T* Mrs = smem_ptr<T>((uint32_t)__cvta_generic_to_shared(after));
+  int32_t* Mis = smem_ptr<int32_t>((uint32_t)__cvta_generic_to_shared(after));
+  after += (size_t)gslice * (normal ? sizeof(T) : sizeof(int32_t));
+  after = reinterpret_cast<unsigned char*>(((uintptr_t)after + 15) & ~(uintptr_t)15);
+  // (offsets that depend on the likelihood hide the address space from the compiler: going through the
+  //  32-bit shared-window address keeps the accesses LDS / STS instead of generic loads)
+  double* Sinv = smem_ptr<double>((uint32_t)__cvta_generic_to_shared(after));   // [gslice] 1 / sigmasq_g (Normal likelihood only)
+  if (normal) after += (size_t)gslice * sizeof(double);
+  double* scratch = smem_ptr<double>((uint32_t)__cvta_generic_to_shared(after));   // [2 * THREADS / 32]
+  double* mail = scratch + 2 * (THREADS / 32);              // [8][2]  partial sums of every block (used in block 0)
+  double* bc = mail + 16;                                   // [2]     {value, flag} from block 0
+  double* sP = bc + 2;                                      // [64] row k of P and of its prior parameters, A, the
+  double* sQ1 = sP + 64;                                    //      zero-row flags: read once, not once per signature
+  double* sQ2 = sQ1 + 64;
+  double* vZ = sQ2 + 64;                                    // [64][P_PRE] base variates of the first attempts of every draw:
+  double* vE = vZ + 64 * P_PRE;                             //   standard normal | -log u (exponential) | log u' (its accept test)
+  double* vU = vE + 64 * P_PRE;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(vU + 64 * P_PRE);   // [2]     "row n of E has landed in buffer n & 1"
+  int* sA = reinterpret_cast<int*>(mbar + 2);               // [64]
+  int* sZ = sA + 64;                                        // [64]
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && ng > 0) {                                  // row 0 of E on its way while the slices are gathered
+    mbar_expect_tx(&mbar[0], e_bytes);
+    bulk_g2s(Eb0, Et + g0, e_bytes, &mbar[0]);
+  }
+  const int iter = d.ctrl->iter;
+  for (int j = tid; j < ng; j += THREADS) {
+    const long long i = k + (long long)K * (g0 + j);
+    Mh[j] = d.Mhat[i];
+    if (normal) { Mrs[j] = d.Mr[i]; Sinv[j] = 1.0 / (double)d.sigmasq[g0 + j]; } else Mis[j] = d.Mi[i];
+  }
+  for (int n = tid; n < N; n += THREADS) {
+    const long long c = k + (long long)K * n;
+    sA[n] = d.A[n];
+    sZ[n] = d.nzE[((iter - 1) & 1) * N + n] == 0;           // all(E[n, ] == 0), R/sample_Pn.R:56
+    sP[n] = (double)d.P[c];
+    if (d.prior == PRIOR_EXPONENTIAL) { sQ1[n] = (double)d.Lambda_p[c]; sQ2[n] = 0.0; }
+    else if (d.prior == PRIOR_TRUNCNORMAL) { sQ1[n] = (double)d.Mu_p[c]; sQ2[n] = (double)d.Sigmasq_p[c]; }
+  }
+  // The N draws of the row are sequential, and one thread evaluating a truncated-normal draw (Philox,
+  // logarithm, square root, cosine) is ~2.5 us of dependent fp64 code with the whole cluster waiting.
+  // What the first attempts consume does not depend on the conditional's moments: evaluate it here,
+  // N x P_PRE threads in parallel (same expressions as truncnorm0_draw, bnmf_rng.cuh).
+  for (int i = tid; i < N * P_PRE; i += THREADS) {
+    const int n = i / P_PRE, t = i - n * P_PRE;
+    const U4 w = make_stream(d.seed, iter, PUR_P, k + (long long)K * n).at((uint32_t)t);
+    vZ[i] = normal_from<double>(w.x, w.y);
+    vE[i] = -tlog<double>(u01<double>(w.x));
+    vU[i] = tlog<double>(u01<double>(w.y));
+  }
+  const bool mh_on = d.MH && d.ctrl->converged;
+  __syncthreads();
+
+  for (int n = 0; n < N; ++n) {
+    const int An = sA[n];
+    const long long c = k + (long long)K * n;
+    const double pkn = sP[n];
+    const bool active = An != 0 && !sZ[n];
+    const T* En = Eb0 + (size_t)(n & 1) * gslice;      // (one base pointer: the loads stay LDS)
+    // the other buffer is free (its last readers passed the barrier that ended signature n-1): prefetch row n+1
+    if (tid == 0 && n + 1 < N && ng > 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&mbar[(n + 1) & 1], e_bytes);
+      bulk_g2s(Eb0 + (size_t)((n + 1) & 1) * gslice, Et + (long long)(n + 1) * Gp + g0, e_bytes, &mbar[(n + 1) & 1]);
+    }
+    if (ng > 0) mbar_wait(&mbar[n & 1], (uint32_t)((n >> 1) & 1));
+    // ---- pass 1: the two sums of the conditional ----
+    double num1 = 0.0, den = 0.0;
+    if (active) {
+#pragma unroll 4
+      for (int j = tid; j < ng; j += THREADS) {
+        const double mh = (double)Mh[j];
+        const double e = (double)En[j];
+        const double inv = normal ? Sinv[j] : 1.0 / mh;
+        const double mh_no = mh - pkn * e;
+        const double m = normal ? (double)Mrs[j] : (double)Mis[j];
+        num1 += e * ((m - mh_no) * inv);
+        den += (e * e) * inv;
+      }
+      block_sum2<THREADS>(num1, den, scratch);
+      if (tid == 0) { dsmem_store(&mail[2 * rank], 0, num1); dsmem_store(&mail[2 * rank + 1], 0, den); }
+    }
+    cluster_sync_all();
+    // ---- block 0 draws ----
+    if (rank == 0 && tid == 0) {
+      const Stream st = make_stream(d.seed, iter, PUR_P, c);
+      double x;
+      if (!active) {
+        x = prior_draw(d, st, 0, c);
+      } else {
+        double s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < CS; ++r) { s1 += mail[2 * r]; s2 += mail[2 * r + 1]; }
+        double mu, v;
+        if (d.prior == PRIOR_EXPONENTIAL) {
+          mu = (s1 - sQ1[n]) / s2; v = 1.0 / s2;
+        } else {
+          const double sg = sQ2[n];
+          s2 = s2 + 1.0 / sg;
+          mu = (s1 + sQ1[n] / sg) / s2; v = 1.0 / s2;
+        }
+        // truncnorm0_draw(st, mu, sqrt(v)) with the variates of attempts 0 .. P_PRE-1 at hand
+        const double sd = sqrt(v);
+        const double alpha = -mu / sd;
+        bool found = false;
+        if (alpha <= 0.45) {
+          double z = alpha;
+          for (int t = 0; t < P_PRE && !found; ++t) { const double zz = vZ[n * P_PRE + t]; if (zz >= alpha) { z = zz; found = true; } }
+          x = mu + sd * z;
+          x = x < 0.0 ? 0.0 : x;
+        } else {
+          const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
+          double e = 0.0;
+          for (int t = 0; t < P_PRE && !found; ++t) {
+            const double ee = vE[n * P_PRE + t] / lam;
+            const double dz = (alpha + ee) - lam;
+            if (vU[n * P_PRE + t] <= -0.5 * (dz * dz)) { e = ee; found = true; }
+          }
+          x = sd * e;
+        }
+        if (!found) x = truncnorm0_draw<double>(st, mu, sd, (uint32_t)P_PRE);
+      }
+      x = (double)(T)x;
+      if (!(mh_on && An != 0)) {
+        if (d.MH && An != 0) d.P_acc[c] = (T)1;                        // R/sample_Pn.R:201-204
+        d.P[c] = (T)x;
+        if (x != 0.0) atomicOr(&d.nzP[n], 1);
+        const double dv = An ? x - pkn : 0.0;
+        for (int r = 0; r < CS; ++r) { dsmem_store(&bc[0], r, dv); dsmem_store(&bc[1], r, 0.0); }
+      } else {
+        for (int r = 0; r < CS; ++r) { dsmem_store(&bc[0], r, x); dsmem_store(&bc[1], r, 1.0); }
+      }
+    }
+    cluster_sync_all();
+    double dv = bc[0];
+    if (bc[1] != 0.0) {
+      // ---- Metropolis-Hastings accept step (R/sample_Pn.R:199-248): log ratio over the row ----
+      const double dp = dv - pkn;          // bc[0] carries the proposal
+      double D = 0.0, zero = 0.0;
+#pragma unroll 2
+      for (int j = tid; j < ng; j += THREADS) {
+        const double mh = (double)Mh[j];
+        const double m = normal ? (double)Mrs[j] : (double)Mis[j];
+        D += mh_cell(m, mh, mh + dp * (double)En[j]);
+      }
+      block_sum2<THREADS>(D, zero, scratch);
+      if (tid == 0) dsmem_store(&mail[2 * rank], 0, D);
+      cluster_sync_all();
+      if (rank == 0 && tid == 0) {
+        double Dt = 0.0;
+        for (int r = 0; r < CS; ++r) Dt += mail[2 * r];
+        const double ratio = mh_ratio(Dt);
+        d.P_acc[c] = (T)ratio;
+        const double u = u01<double>(make_stream(d.seed, iter, PUR_MH_P, c).at(0).x);
+        const double xn = u < ratio ? dv : pkn;
+        d.P[c] = (T)xn;
+        if (xn != 0.0) atomicOr(&d.nzP[n], 1);
+        for (int r = 0; r < CS; ++r) dsmem_store(&bc[0], r, xn - pkn);
+      }
+      cluster_sync_all();
+      dv = bc[0];
+    }
+    // ---- rank-1 correction of the slice (every later conditional sees the new column) ----
+    if (dv != 0.0) {
+#pragma unroll 4
+      for (int j = tid; j < ng; j += THREADS) Mh[j] = (T)((double)Mh[j] + dv * (double)En[j]);
+    }
+    __syncthreads();   // buffer n & 1 and Mh are settled before the next prefetch / pass
+    // (bc / mail are rewritten only after the next cluster barrier, which every block reaches
+    //  after it has read them)
+  }
+  for (int j = tid; j < ng; j += THREADS) d.Mhat[k + (long long)K * (g0 + j)] = Mh[j];
+  if (rank == 0 && tid == 0) d.dvec[k] = 0.0;
+}
+
+// ------------------------------------------------------------------------------
 // k_e_sweep: all N updates of E[., g] for one genome per warp.  The genome's column of M
 // and of the running Mhat stay in shared memory for the whole sweep; column n of P is
 // staged once per block and shared by its warps; the reductions over k are warp

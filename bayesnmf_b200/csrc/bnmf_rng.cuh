@@ -173,11 +173,12 @@ template <typename T> BNMF_HD_CALL T gamma_draw(const Stream s, T shape, T rate,
 //                   formed as sd*(z-alpha) directly so a mean far below zero does
 //                   not cancel catastrophically.
 // Attempt t consumes Philox block t: (x,y) -> normal or (x -> exp, y -> accept).
-template <typename T> BNMF_HD_CALL T truncnorm0_draw(const Stream s, T mean, T sd) {
+// t0 = first attempt to try (callers that have already evaluated attempts 0 .. t0-1 themselves).
+template <typename T> BNMF_HD_CALL T truncnorm0_draw(const Stream s, T mean, T sd, uint32_t t0 = 0) {
   const T alpha = -mean / sd;
   if (alpha <= (T)0.45) {
     T z = alpha;
-    for (uint32_t t = 0; t < 4096u; ++t) {
+    for (uint32_t t = t0; t < 4096u; ++t) {
       U4 w = s.at(t);
       T zz = normal_from<T>(w.x, w.y);
       if (zz >= alpha) { z = zz; break; }
@@ -187,7 +188,7 @@ template <typename T> BNMF_HD_CALL T truncnorm0_draw(const Stream s, T mean, T s
   }
   const T lam = (T)0.5 * (alpha + tsqrt<T>(alpha * alpha + (T)4));
   T e = (T)0;
-  for (uint32_t t = 0; t < 4096u; ++t) {
+  for (uint32_t t = t0; t < 4096u; ++t) {
     U4 w = s.at(t);
     T ee = -tlog<T>(u01<T>(w.x)) / lam;   // z - alpha
     T dz = (alpha + ee) - lam;
