@@ -296,9 +296,10 @@ struct Sampler : bnmf_handle {
     n_ktiles = (K + KT - 1) / KT;
     const int cts = (int)((G + 31) / 32);
     // rows per work item: an item costs ~12k cycles of fixed latency (E tile in, SE out, the queue
-    // atomic), so items are as coarse as leaves every resident warp (148 SMs x 16) three of them
+    // atomic), rows differ widely in their counts: as coarse as leaves every resident warp
+    // (148 SMs x 16) about eight items to balance with (measured at 12.5k .. 100k genomes)
     ZR = 32;
-    while (ZR > 1 && (long long)cts * ((K + ZR - 1) / ZR) < 3LL * 148 * 16) ZR >>= 1;
+    while (ZR > 1 && (long long)cts * ((K + ZR - 1) / ZR) < 7LL * 148 * 16) ZR >>= 1;
     if (const char* e = getenv("BNMF_ZR")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ZR = v; }   // tuning knob
     if (ZR > KT) ZR = KT;
     d.n_zitems = cts * n_ktiles * ((KT + ZR - 1) / ZR);

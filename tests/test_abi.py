@@ -69,3 +69,18 @@ def test_null_arguments_fail_cleanly(built_lib):
     assert L.bnmf_create(None, None, None) != 0
     assert b"null" in L.bnmf_last_error()
     assert L.bnmf_step(None, 1, 0, None, None, None) != 0
+
+
+def test_r_veneer_compiles_against_stub_and_uses_exported_entries():
+    """r/rcall.c (the .Call veneer a maintainer adds to the reference) parses against a stub of R's C
+    API and calls only entry points that include/bnmf.h declares."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "r", "rcall.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-I" + os.path.join(root, "tests", "stubs"), "-I" + os.path.join(root, "include"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    used = set(re.findall(r"\b(bnmf_[a-z_0-9]+)\s*\(", open(src).read()))
+    declared = set(re.findall(r"\b(bnmf_[a-z_0-9]+)\s*\(", open(os.path.join(root, "include", "bnmf.h")).read()))
+    assert used and used <= declared, used - declared
