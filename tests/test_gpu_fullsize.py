@@ -1,0 +1,101 @@
+"""Properties of the CUDA path at the full sizes of BASELINE.json (where the numpy oracle would
+take minutes), through the C ABI: conservation of the latent counts, independence of the draws
+from the shard decomposition, and a bit-exact oracle check of a slice at an arbitrary genome
+offset.  Plus: the two implementations of the P sweep (cluster-resident rows, pass per signature)
+against each other on a row that spans several thread blocks."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import synth_counts
+
+pytestmark = pytest.mark.gpu
+
+
+def _handle(M, N, **kw):
+    from bayesnmf_b200 import Handle
+    return Handle(M, N, likelihood="poisson", prior="gamma", MH=False, seed=9, **kw)
+
+
+def test_c3_full_size_latent_count_margins(built_lib):
+    """C3 shape (96 x 100,000, N = 20): sum_n SE[n,g] = colSums(M), sum_n SP[k,n] = rowSums(M)
+    wherever Mhat > 0 (R/sample_params.R:253-265), reproducible, and identical for a shard."""
+    from oracle.gibbs import sample_Z_stats
+    K, G, N = 96, 100_000, 20
+    M, _, _ = synth_counts(K, G, N, 4000.0, seed=3)
+    rng = np.random.default_rng(1)
+    P = rng.gamma(1.0, 0.02, size=(K, N))
+    E = rng.gamma(1.0, 4000.0 / N, size=(N, G))
+    A = np.ones(N); A[3] = 0
+    h = _handle(M, N)
+    h.set_state("P", P); h.set_state("E", E); h.set_state("A", A)
+    h.sample_z(4)
+    SP, SE = h.get_state("SP"), h.get_state("SE")
+    assert np.array_equal(SE.sum(axis=0), M.sum(axis=0))
+    assert np.array_equal(SP.sum(axis=1), M.sum(axis=1))
+    assert SP[:, 3].sum() == 0 and SE[3].sum() == 0          # an excluded signature gets no counts
+    h.sample_z(4)
+    assert np.array_equal(SP, h.get_state("SP")) and np.array_equal(SE, h.get_state("SE"))
+    h.close()
+    # a shard [g0, g1) of the same problem draws the same counts (Philox is keyed by the global cell)
+    g0, g1 = 41_237, 47_301
+    hs = _handle(M[:, g0:g1], N, g0=g0, G_total=G)
+    hs.set_state("P", P); hs.set_state("E", E[:, g0:g1]); hs.set_state("A", A)
+    hs.sample_z(4)
+    assert np.array_equal(hs.get_state("SE"), SE[:, g0:g1])
+    hs.close()
+    # and the oracle agrees bit for bit on a slice of it
+    s0, s1 = 41_300, 41_364
+    oSP, oSE = sample_Z_stats(M[:, s0:s1], P, A, E[:, s0:s1], seed=9, it=4, g0=s0)
+    assert np.array_equal(oSE, SE[:, s0:s1])
+
+
+def test_c3_full_size_iterations_conserve_counts(built_lib):
+    """Three full Gibbs iterations at the C3 shape: every iteration's margins add up to the data,
+    metrics are finite and the log-likelihood improves on the prior draw."""
+    from bayesnmf_b200.hyperpriors import fill_hyperprior_params
+    K, G, N = 96, 100_000, 20
+    M, _, _ = synth_counts(K, G, N, 4000.0, seed=4)
+    h = _handle(M, N)
+    for k, v in fill_hyperprior_params(None, "gamma", float(M.mean()), N).items():
+        h.set_hyper(k, v)
+    row1 = h.init_from_prior()
+    out = h.step(3)
+    assert np.isfinite(out["metrics"]).all()
+    assert out["metrics"][-1][3] > row1["loglikelihood"]
+    SP, SE = h.get_state("SP"), h.get_state("SE")
+    assert SP.sum() == SE.sum() == M.sum()
+    assert np.array_equal(SE.sum(axis=0), M.sum(axis=0))
+    h.close()
+
+
+@pytest.mark.parametrize("lik,prior,MH", [("poisson", "exponential", True), ("normal", "truncnormal", False)])
+def test_p_sweep_rows_equal_passes(built_lib, lik, prior, MH):
+    """k_p_rows (a cluster of blocks per mutation type, rows resident in shared memory) and the
+    pass-per-signature kernels implement the same conditionals with different summation orders:
+    states agree to 1e-9 relative over several iterations, before and after `converged`.
+    G is large enough that a row spans several blocks of a cluster."""
+    from bayesnmf_b200 import Handle
+    K, G, N = 6, 40_000, 4
+    M, _, _ = synth_counts(K, G, N, 600.0, seed=2)
+    if lik == "normal":
+        M = M + np.random.default_rng(5).normal(0.0, 1.0, M.shape)
+    res = []
+    for rows in ("1", "0"):
+        os.environ["BNMF_P_ROWS"] = rows
+        try:
+            h = Handle(M, N, likelihood=lik, prior=prior, MH=MH, seed=4)
+        finally:
+            os.environ.pop("BNMF_P_ROWS", None)
+        h.init_from_prior()
+        h.step(3)
+        out = h.step(2, converged=True) if MH else h.step(2)
+        res.append((h.get_state("P"), h.get_state("E"), h.get_state("Mhat"), out["metrics"][-1], h.timing()["launches"]))
+        h.close()
+    (P1, E1, H1, m1, l1), (P0, E0, H0, m0, l0) = res
+    assert l1 < l0                                             # the cluster kernel replaced 2N (4N) launches
+    np.testing.assert_allclose(P1, P0, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(E1, E0, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(H1, H0, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(m1, m0, rtol=1e-9, atol=1e-9, equal_nan=True)

@@ -176,3 +176,28 @@ def test_get_mode_and_MAP():
     for p, e in zip(P, E):                      # renormalize keeps the product
         rp, re = og.renormalize(p, e)
         np.testing.assert_allclose(rp @ re, p @ e, rtol=1e-12)
+
+
+def test_z_thresholds_contract_edges():
+    """Integer pick thresholds of the latent-count draw (csrc/bnmf_poisson.cuh, oracle z_thresholds):
+    monotone, 0 for leading zero-probability categories, saturated at 2^32 - 1 once the CDF reaches
+    the total (so a trailing zero-probability category is never picked), NaN -> 0 when the total is 0."""
+    from oracle.gibbs import z_cdf, z_thresholds, sample_Z_stats
+    P = np.array([[0.0, 0.2, 0.0, 0.8, 0.0]])                 # K = 1, N = 5
+    E = np.ones((5, 3)); E[:, 2] = 0.0                        # third genome: all probabilities zero
+    A = np.ones(5)
+    cdf = z_cdf(P, A, E)
+    thr = z_thresholds(cdf, 5)
+    assert thr.shape == (1, 4, 3)
+    assert (np.diff(thr.astype(np.int64), axis=1) >= 0).all()
+    assert thr[0, 0, 0] == 0                                  # category 0 has no mass: always skipped
+    assert thr[0, 1, 0] == thr[0, 2, 0] == np.uint64(int(0.2 * 2 ** 32))
+    assert thr[0, 3, 0] == 0xFFFFFFFF                         # CDF complete: category 4 unreachable
+    assert (thr[0, :, 2] == 0).all()                          # 0/0 -> NaN -> 0 (cell has no picks anyway)
+    M = np.array([[1000, 7, 5]])
+    SP, SE, Z = sample_Z_stats(M, P, A, E, seed=1, it=2, return_Z=True)
+    assert Z[0, [0, 2, 4], :].sum() == 0 and Z[0, :, 2].sum() == 0
+    assert Z[0, :, 0].sum() == 1000 and abs(Z[0, 1, 0] - 200) < 60
+    # float32 state: same construction in float32 arithmetic
+    thr32 = z_thresholds(z_cdf(P, A, E, f32=True), 5, f32=True)
+    assert thr32[0, 3, 0] == 0xFFFFFFFF and thr32[0, 0, 0] == 0
