@@ -2,7 +2,7 @@
 // likelihood with Metropolis-Hastings proposals, and rank learning (SBFI / BFI).
 //
 //   prior parameters   R/sample_priors.R:214-308          k_hyper
-//   P sweep            R/sample_Pn.R:54-87,132-248        k_p_pass1 -> k_p_draw [-> k_p_pass2 -> k_p_accept]   per signature
+//   P sweep            R/sample_Pn.R:54-87,132-248        k_p_rows (one launch, a cluster per mutation type)  |  k_p_pass1 -> k_p_draw [-> k_p_pass2 -> k_p_accept]   per signature
 //   E sweep            R/sample_En.R:54-86,131-241        k_e_sweep                                            one launch
 //   R, A sweep         R/sample_params.R:101-241          k_r -> (k_a_pass -> k_a_draw)                        per signature
 //   sigmasq + metrics  R/sample_params.R:275-286, R/utils.R:412-455     k_final, k_pprior
