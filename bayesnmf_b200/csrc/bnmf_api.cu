@@ -190,6 +190,9 @@ struct Sampler : bnmf_handle {
     if (gexec) cudaGraphExecDestroy(gexec);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -242,7 +245,14 @@ struct Sampler : bnmf_handle {
     if (cfg.N > 64) return fail("bnmf_create: N = %d > 64 is not supported by this build", cfg.N);
     if (cfg.G > 2000000000LL / (cfg.K > cfg.N ? cfg.K : cfg.N)) { /* 64-bit indexing is used throughout; fine */ }
     CK(cudaSetDevice(cfg.device));
-    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    {
+      int least = 0, greatest = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, greatest));
+      CK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, least));
+      CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     lap("stream + events");
     memset(&d, 0, sizeof(d));
@@ -591,6 +601,15 @@ struct Sampler : bnmf_handle {
 
   // ---- the iteration ---------------------------------------------------------------
   int launches = 0;
+  // Overlap of the E side's hyper-draws of iteration t+1 with k_zstat of iteration t (k_eside_hyper):
+  // a low-priority side stream, fork / join events, the host's copy of the iteration counter.
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool hyper_ready = false, spec_next = false;
+  int h_iter = 0;
+  bool overlap_allowed() const {
+    static const bool off = getenv("BNMF_OVERLAP") && !strcmp(getenv("BNMF_OVERLAP"), "0");
+    return !off && side != nullptr && cfg.prior == BNMF_GAMMA && cfg.likelihood == BNMF_POISSON && !cfg.MH && !graphs_allowed();
+  }
   int mh_setup();
   int mh_iteration(int from_prior, uint32_t have);
   int poisson_iteration(int from_prior, uint32_t have, cudaEvent_t z0, cudaEvent_t z1) {
@@ -603,7 +622,19 @@ struct Sampler : bnmf_handle {
       case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
               k_eside<T, ET, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
       case 2: k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              k_eside<T, ET, PRIOR_GAMMA, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
+              if (hyper_ready) {          // Beta_e / Alpha_e of this iteration were drawn under the previous k_zstat
+                CK(cudaStreamWaitEvent(stream, ev_join, 0));
+                k_eside<T, ET, PRIOR_GAMMA, 0, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE);
+                hyper_ready = false;
+              } else k_eside<T, ET, PRIOR_GAMMA, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE);
+              if (spec_next && overlap_allowed()) {
+                CK(cudaEventRecord(ev_fork, stream));
+                CK(cudaStreamWaitEvent(side, ev_fork, 0));
+                k_eside_hyper<T, 256><<<blocks((long long)cfg.N * cfg.G, 256), 256, 0, side>>>(d, h_iter + 1);
+                CK(cudaEventRecord(ev_join, side));
+                hyper_ready = true; ++launches;
+              }
+              break;
       default: k_pside<T, 128, PRIOR_GAMMA, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
                k_eside<T, ET, PRIOR_GAMMA, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
     }
@@ -743,6 +774,12 @@ struct Sampler : bnmf_handle {
     last_z_ms = 0; last_iter_ms = 0;
     const bool use_graph = graphs_allowed();
     if (use_graph) { if (ensure_graph(P_out != nullptr, A_out != nullptr)) return 1; }
+    if (overlap_allowed()) {     // the host's copy of state$iter (the side stream's draws are keyed by it)
+      Ctrl hc; CK(cudaMemcpyAsync(&hc, d.ctrl, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      h_iter = hc.iter;
+    }
+    hyper_ready = false;
     CK(cudaEventRecord(ev0, stream));
     int done = 0;
     while (done < n_iters) {
@@ -756,6 +793,8 @@ struct Sampler : bnmf_handle {
       for (int i = 0; i < chunk; ++i) {
         if (flush_bytes) CK(cudaMemsetAsync(flush_buf, i & 0xff, flush_bytes, stream));
         CK(cudaEventRecord(iev[2 * i], stream));
+        spec_next = done + i + 1 < n_iters;     // never past the end of this call: the state handed back is iteration n's
+        ++h_iter;
         if (use_graph) { CK(cudaGraphLaunch(gexec, stream)); launches += glaunches; }
         else if (launch_iteration(P_out != nullptr, A_out != nullptr, timez ? zev[2 * i] : nullptr, timez ? zev[2 * i + 1] : nullptr)) return 1;
         CK(cudaEventRecord(iev[2 * i + 1], stream));

@@ -136,9 +136,34 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
 //   rowSums(E) (fixed point, order-independent), sum log prior(E)   (R/utils.R:168-173)
 // Consumes and clears SE.  Block b writes its partial to epart[b].
 // ------------------------------------------------------------------------------
-template <typename T, int THREADS, int PRIOR, int FROM_PRIOR>
+// k_eside_hyper: the two hyper-draws of the gamma prior on the E side for iteration `iter`,
+//   Beta_e[n,g]  ~ Gamma(A_e + Alpha_e, B_e + E)                      (R/sample_priors.R:325-344)
+//   Alpha_e[n,g] ~ its log-concave conditional given the new Beta_e    (R/sample_priors.R:356-397)
+// as a kernel of their own.  They read nothing but E and the prior parameters of the previous
+// iteration -- not P, not the latent counts -- so the host launches them for iteration t+1 on a
+// low-priority side stream while k_zstat of iteration t is running: the fp64 pipe that k_zstat
+// leaves idle does 3/4 of the E side's work for free (64 registers x 256 threads fit next to the
+// two k_zstat blocks of an SM).  k_eside<..., HYPER_DONE = 1> then takes the values as stored.
+// `iter` comes by value: the device's counter may already have moved on when a block starts.
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_eside_hyper(Dev<T> d, int iter) {
+  const long long cells = (long long)d.N * d.G;
+  const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
+  const long long ii = idx < cells ? idx : cells - 1;     // the whole block runs the staged sampler (its barriers)
+  const long long c = (ii % d.N) + (long long)d.N * (d.g0 + ii / d.N);
+  const double al0 = (double)d.Alpha_e[ii], Eold = (double)d.E[ii];
+  const double be = (double)(T)gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
+                                                  (double)d.A_e.at(ii) + al0, (double)d.B_e.at(ii) + Eold);
+  __syncthreads();
+  const double al = (double)(T)alpha_draw<true>(make_stream(d.seed, iter, PUR_HYP_E2, c),
+                                                (double)d.C_e.at(ii), (double)d.D_e.at(ii), be, Eold, al0);
+  if (idx < cells) { d.Beta_e[ii] = (T)be; d.Alpha_e[ii] = (T)al; }
+}
+
+template <typename T, int THREADS, int PRIOR, int FROM_PRIOR, int HYPER_DONE = 0>
 __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
-  constexpr int from_prior = FROM_PRIOR;
+  constexpr int from_prior = FROM_PRIOR || HYPER_DONE;      // (hyper-draws already made: take them as stored)
+  constexpr int prior_draw_only = FROM_PRIOR;
   __shared__ double scratch[THREADS / 32];
   __shared__ long long fx[THREADS];
   const int N = d.N;
@@ -174,7 +199,7 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
       }
       if (!keepE) {
         double shape = al, rate = be;
-        if (!from_prior) { shape += (double)d.SE[ii]; rate += csP; }
+        if (!prior_draw_only) { shape += (double)d.SE[ii]; rate += csP; }
         Enew = gamma_draw<double>(make_stream(d.seed, iter, PUR_E, c), shape, rate);
       }
       __syncthreads();
@@ -189,7 +214,7 @@ __global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
       }
       if (!keepE) {
         double shape = 1.0, rate = la;
-        if (!from_prior) { shape += (double)d.SE[ii]; rate += csP; }
+        if (!prior_draw_only) { shape += (double)d.SE[ii]; rate += csP; }
         Enew = gamma_draw<double>(make_stream(d.seed, iter, PUR_E, c), shape, rate);
       }
       lp = dexp_log((double)(T)Enew, (double)(T)la);
