@@ -193,6 +193,7 @@ struct Sampler : bnmf_handle {
     if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_join_p) cudaEventDestroy(ev_join_p);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -252,6 +253,7 @@ struct Sampler : bnmf_handle {
       CK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, least));
       CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_join_p, cudaEventDisableTiming));
     }
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     lap("stream + events");
@@ -603,7 +605,7 @@ struct Sampler : bnmf_handle {
   int launches = 0;
   // Overlap of the E side's hyper-draws of iteration t+1 with k_zstat of iteration t (k_eside_hyper):
   // a low-priority side stream, fork / join events, the host's copy of the iteration counter.
-  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_p = nullptr;
   bool hyper_ready = false, spec_next = false;
   int h_iter = 0;
   bool overlap_allowed() const {
@@ -621,8 +623,11 @@ struct Sampler : bnmf_handle {
               k_eside<T, ET, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
       case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
               k_eside<T, ET, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
-      case 2: k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              if (hyper_ready) {          // Beta_e / Alpha_e of this iteration were drawn under the previous k_zstat
+      case 2: if (hyper_ready) {          // Beta_p / Alpha_p of this iteration were drawn under the previous k_zstat
+                CK(cudaStreamWaitEvent(stream, ev_join_p, 0));
+                k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
+              } else k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
+              if (hyper_ready) {          // ... and so were Beta_e / Alpha_e
                 CK(cudaStreamWaitEvent(stream, ev_join, 0));
                 k_eside<T, ET, PRIOR_GAMMA, 0, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE);
                 hyper_ready = false;
@@ -630,9 +635,17 @@ struct Sampler : bnmf_handle {
               if (spec_next && overlap_allowed()) {
                 CK(cudaEventRecord(ev_fork, stream));
                 CK(cudaStreamWaitEvent(side, ev_fork, 0));
-                k_eside_hyper<T, 256><<<blocks((long long)cfg.N * cfg.G, 256), 256, 0, side>>>(d, h_iter + 1);
+                k_pside_hyper<T, 128><<<cfg.N, 128, 0, side>>>(d, h_iter + 1);
+                CK(cudaEventRecord(ev_join_p, side));
+                {
+                  static const int ht = getenv("BNMF_HYPER_THREADS") ? atoi(getenv("BNMF_HYPER_THREADS")) : 256;
+                  const long long ncell = (long long)cfg.N * cfg.G;
+                  if (ht == 128) k_eside_hyper<T, 128><<<blocks(ncell, 128), 128, 0, side>>>(d, h_iter + 1);
+                  else if (ht == 512) k_eside_hyper<T, 512><<<blocks(ncell, 512), 512, 0, side>>>(d, h_iter + 1);
+                  else k_eside_hyper<T, 256><<<blocks(ncell, 256), 256, 0, side>>>(d, h_iter + 1);
+                }
                 CK(cudaEventRecord(ev_join, side));
-                hyper_ready = true; ++launches;
+                hyper_ready = true; launches += 2;
               }
               break;
       default: k_pside<T, 128, PRIOR_GAMMA, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);

@@ -67,9 +67,28 @@ __global__ void k_begin_iter(Dev<T> d, int* work_ctr, int n_ctr) {
 // from_prior = 1 draws P from its prior (R/sample_Pn.R:12-30) and skips the
 // hyper-updates; keepP = 1 leaves a user-supplied P untouched (skip = names(init_params)).
 // ------------------------------------------------------------------------------
-template <typename T, int THREADS, int PRIOR, int FROM_PRIOR>
+// k_pside_hyper: Beta_p / Alpha_p of iteration `iter` from P and the prior parameters of the
+// iteration before (R/sample_priors.R:284-324, :356-390); like k_eside_hyper it runs on the side
+// stream under the previous k_zstat, which takes two of the three samplers of k_pside off the
+// critical path of an iteration (one block per signature: pure latency).
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_pside_hyper(Dev<T> d, int iter) {
+  const int n = blockIdx.x, K = d.K;
+  for (int k = threadIdx.x; k < K; k += THREADS) {
+    const long long c = (long long)k + (long long)K * n;
+    const double Pold = (double)d.P[c], al0 = (double)d.Alpha_p[c];
+    const double be = (double)(T)gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_P1, c),
+                                                    (double)d.A_p.at(c) + al0, (double)d.B_p.at(c) + Pold);
+    const double al = (double)(T)alpha_draw(make_stream(d.seed, iter, PUR_HYP_P2, c),
+                                            (double)d.C_p.at(c), (double)d.D_p.at(c), be, Pold, al0);
+    d.Beta_p[c] = (T)be; d.Alpha_p[c] = (T)al;
+  }
+}
+
+template <typename T, int THREADS, int PRIOR, int FROM_PRIOR, int HYPER_DONE = 0>
 __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
-  constexpr int from_prior = FROM_PRIOR;
+  constexpr int from_prior = FROM_PRIOR || HYPER_DONE;      // (hyper-draws already made: take them as stored)
+  constexpr int prior_draw_only = FROM_PRIOR;
   __shared__ double scratch[THREADS / 32];
   const int n = blockIdx.x;
   const int K = d.K, N = d.N;
@@ -94,7 +113,7 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
       }
       if (!keepP) {
         double shape = al, rate = be;
-        if (!from_prior) { shape += (double)d.SP[c]; rate += An ? rsE : 0.0; }
+        if (!prior_draw_only) { shape += (double)d.SP[c]; rate += An ? rsE : 0.0; }
         Pnew = gamma_draw<double>(make_stream(d.seed, iter, PUR_P, c), shape, rate);
       }
       lpc = dgamma_log((double)(T)Pnew, (double)(T)al, (double)(T)be);
@@ -107,7 +126,7 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
       }
       if (!keepP) {
         double shape = 1.0, rate = la;
-        if (!from_prior) { shape += (double)d.SP[c]; rate += An ? rsE : 0.0; }
+        if (!prior_draw_only) { shape += (double)d.SP[c]; rate += An ? rsE : 0.0; }
         Pnew = gamma_draw<double>(make_stream(d.seed, iter, PUR_P, c), shape, rate);
       }
       lpc = dexp_log((double)(T)Pnew, (double)(T)la);
