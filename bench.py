@@ -198,6 +198,16 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         warm = float(t[0])
     last_row = out["metrics"][-1]
+    # the latent-count kernel on its own (inside an iteration it shares the SMs with the side stream's
+    # hyper-draws of the next iteration, which lengthens its launches and shortens the iteration)
+    z_alone_ms = None
+    if w["likelihood"] == "poisson" and not w["MH"]:
+        zs = [h.sample_z(10_000 + i) for i in range(5)]
+        z_alone_ms = float(np.median(zs[1:]))
+        if world > 1:
+            t = torch.tensor([z_alone_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            z_alone_ms = float(t[0])
 
     # end to end through the public API from HOST buffers: construct (uploads the count
     # matrix), the prior draw, `steps` iterations with every sample_metrics row and every
@@ -247,6 +257,8 @@ def run_b200(args):
         "roofline": {"kernel": "k_zstat", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic("k_zstat", args.workload, prec, world), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": zb, "avg_launch_ms": z_avg_ms,
+                     "launch_ms_kernel_alone": z_alone_ms,
+                     "frac_kernel_alone": (zb / 1e9 / (z_alone_ms * 1e-3) / peak) if z_alone_ms else None,
                      "share_of_step": z_ms / iter_ms if iter_ms else None,
                      "limiters_ncu": ncu_limiters("k_zstat", args.workload, prec, world),
                      "latent_picks_per_s": float(M[:, g_lo:g_hi].sum()) / (z_avg_ms * 1e-3) if z_avg_ms > 0 else None},
