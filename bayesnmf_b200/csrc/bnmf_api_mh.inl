@@ -38,10 +38,14 @@ template <typename T> int Sampler<T>::mh_setup() {
   if (dalloc(&d.ppart, (long long)d.n_gchunks * K * 2) || dalloc(&d.apart, 2LL * col_blocks)) return 1;
   // E sweep: warps per block limited by the shared-memory columns
   const size_t budget = 220 * 1024;
-  long long w = ((long long)(budget / sizeof(double)) - K) / (2LL * K);
-  if (w < 1) return fail("k_e_sweep: K = %d does not fit one genome column in shared memory", K);
-  e_wpb = (int)std::min<long long>(8, w);
-  e_smem = (size_t)(1 + 2 * e_wpb) * K * sizeof(double);
+  // (the variates of the draws are staged only where that does not cost a resident warp: with long
+  //  columns the sweep is bound by the reductions over K, not by the latency of a draw)
+  const long long w0 = ((long long)(budget / sizeof(double)) - K) / (2LL * K + e_sweep_extra(N, 0));
+  const long long w1 = ((long long)(budget / sizeof(double)) - K) / (2LL * K + e_sweep_extra(N, 1));
+  if (w0 < 1) return fail("k_e_sweep: K = %d does not fit one genome column in shared memory", K);
+  e_stage = std::min<long long>(8, w1) >= std::min<long long>(8, w0) ? 1 : 0;
+  e_wpb = (int)std::min<long long>(8, e_stage ? w1 : w0);
+  e_smem = ((size_t)(1 + 2 * e_wpb) * K + (size_t)e_wpb * e_sweep_extra(N, e_stage)) * sizeof(double);
   CK(cudaFuncSetAttribute(k_e_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
   // Row-resident P sweep: a cluster of CS blocks per mutation type keeps the row of M and Mhat in
   // shared memory.  CS is the cluster size that needs the fewest waves of clusters over the K rows
@@ -158,7 +162,7 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
         launches += 2;
       }
     }
-    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, pr_cs ? -1 : N - 1); ++launches;
+    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, pr_cs ? -1 : N - 1, e_stage); ++launches;
     int pending = -1;
     if (cfg.learning_rank) { if (rank_sweep_kernels(&pending)) return 1; }
     k_final<T><<<col_blocks, 256, 0, stream>>>(d, pending, 0); ++launches;

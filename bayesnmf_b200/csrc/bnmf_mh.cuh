@@ -85,6 +85,45 @@ __device__ __forceinline__ double prior_logdens(const Dev<T>& d, int side, long 
   return dgamma_log(x, (double)(side == 0 ? d.Alpha_p : d.Alpha_e)[idx], (double)(side == 0 ? d.Beta_p : d.Beta_e)[idx]);
 }
 
+// ---- truncated-normal draws with the first attempts' variates computed up front ------------------
+// What attempt t of truncnorm0_draw (bnmf_rng.cuh) consumes -- a standard normal, or an exponential
+// and the logarithm of its accept uniform -- does not depend on the moments of the conditional.  The
+// sweeps draw N conditionals one after the other per row / column; evaluating Philox, logarithm,
+// square root and cosine inside that chain costs ~2.5 us per draw with everything else waiting, so
+// the variates of attempts 0 .. P_PRE-1 of all N draws are evaluated beforehand, in parallel, and
+// the chain only selects.  Same expressions, same results as truncnorm0_draw.
+constexpr int P_PRE = 4;
+__device__ __forceinline__ void tn_variates(const Stream& st, int t, double& z, double& e, double& u) {
+  const U4 w = st.at((uint32_t)t);
+  z = normal_from<double>(w.x, w.y);
+  e = -tlog<double>(u01<double>(w.x));
+  u = tlog<double>(u01<double>(w.y));
+}
+// vZ, vE, vU: the P_PRE variates of this draw
+__device__ __forceinline__ double truncnorm0_staged(const Stream& st, double mu, double sd,
+                                                    const double* vZ, const double* vE, const double* vU) {
+  const double alpha = -mu / sd;
+  bool found = false;
+  double x;
+  if (alpha <= 0.45) {
+    double z = alpha;
+    for (int t = 0; t < P_PRE && !found; ++t) { const double zz = vZ[t]; if (zz >= alpha) { z = zz; found = true; } }
+    x = mu + sd * z;
+    x = x < 0.0 ? 0.0 : x;
+  } else {
+    const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
+    double e = 0.0;
+    for (int t = 0; t < P_PRE && !found; ++t) {
+      const double ee = vE[t] / lam;
+      const double dz = (alpha + ee) - lam;
+      if (vU[t] <= -0.5 * (dz * dz)) { e = ee; found = true; }
+    }
+    x = sd * e;
+  }
+  if (!found) x = truncnorm0_draw<double>(st, mu, sd, (uint32_t)P_PRE);
+  return x;
+}
+
 // ------------------------------------------------------------------------------
 // k_hyper: prior-parameter updates of the truncated-normal and exponential priors,
 // element-wise (they read only the previous P / E; R/sample_priors.R:214-308).
@@ -393,8 +432,6 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
   }
 }
 
-// attempts of every truncated-normal draw of a row whose base variates are computed up front, in parallel
-constexpr int P_PRE = 4;
 // bytes of shared memory of k_p_rows for a slice of gslice genomes (gslice a multiple of 16 / sizeof(T))
 template <typename T> __host__ __device__ inline size_t p_rows_smem(int gslice, int threads, bool normal) {
   return (size_t)gslice * (3 * sizeof(T) + (normal ? sizeof(T) + sizeof(double) : sizeof(int32_t))) + 16 +
@@ -461,16 +498,10 @@ __global__ void __launch_bounds__(THREADS) k_p_rows(Dev<T> d, const T* __restric
     if (d.prior == PRIOR_EXPONENTIAL) { sQ1[n] = (double)d.Lambda_p[c]; sQ2[n] = 0.0; }
     else if (d.prior == PRIOR_TRUNCNORMAL) { sQ1[n] = (double)d.Mu_p[c]; sQ2[n] = (double)d.Sigmasq_p[c]; }
   }
-  // The N draws of the row are sequential, and one thread evaluating a truncated-normal draw (Philox,
-  // logarithm, square root, cosine) is ~2.5 us of dependent fp64 code with the whole cluster waiting.
-  // What the first attempts consume does not depend on the conditional's moments: evaluate it here,
-  // N x P_PRE threads in parallel (same expressions as truncnorm0_draw, bnmf_rng.cuh).
+  // variates of the first attempts of the row's N draws, N x P_PRE threads in parallel (tn_variates)
   for (int i = tid; i < N * P_PRE; i += THREADS) {
     const int n = i / P_PRE, t = i - n * P_PRE;
-    const U4 w = make_stream(d.seed, iter, PUR_P, k + (long long)K * n).at((uint32_t)t);
-    vZ[i] = normal_from<double>(w.x, w.y);
-    vE[i] = -tlog<double>(u01<double>(w.x));
-    vU[i] = tlog<double>(u01<double>(w.y));
+    tn_variates(make_stream(d.seed, iter, PUR_P, k + (long long)K * n), t, vZ[i], vE[i], vU[i]);
   }
   const bool mh_on = d.MH && d.ctrl->converged;
   __syncthreads();
@@ -522,26 +553,7 @@ __global__ void __launch_bounds__(THREADS) k_p_rows(Dev<T> d, const T* __restric
           s2 = s2 + 1.0 / sg;
           mu = (s1 + sQ1[n] / sg) / s2; v = 1.0 / s2;
         }
-        // truncnorm0_draw(st, mu, sqrt(v)) with the variates of attempts 0 .. P_PRE-1 at hand
-        const double sd = sqrt(v);
-        const double alpha = -mu / sd;
-        bool found = false;
-        if (alpha <= 0.45) {
-          double z = alpha;
-          for (int t = 0; t < P_PRE && !found; ++t) { const double zz = vZ[n * P_PRE + t]; if (zz >= alpha) { z = zz; found = true; } }
-          x = mu + sd * z;
-          x = x < 0.0 ? 0.0 : x;
-        } else {
-          const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
-          double e = 0.0;
-          for (int t = 0; t < P_PRE && !found; ++t) {
-            const double ee = vE[n * P_PRE + t] / lam;
-            const double dz = (alpha + ee) - lam;
-            if (vU[n * P_PRE + t] <= -0.5 * (dz * dz)) { e = ee; found = true; }
-          }
-          x = sd * e;
-        }
-        if (!found) x = truncnorm0_draw<double>(st, mu, sd, (uint32_t)P_PRE);
+        x = truncnorm0_staged(st, mu, sqrt(v), vZ + n * P_PRE, vE + n * P_PRE, vU + n * P_PRE);
       }
       x = (double)(T)x;
       if (!(mh_on && An != 0)) {
@@ -602,14 +614,25 @@ __global__ void __launch_bounds__(THREADS) k_p_rows(Dev<T> d, const T* __restric
 // staged once per block and shared by its warps; the reductions over k are warp
 // butterflies (fixed order).  One streaming pass over M and Mhat per iteration, whatever N.
 // ------------------------------------------------------------------------------
+// doubles of shared memory per warp of k_e_sweep besides its two columns: the genome's column of E
+// and of the prior parameters, and the variates of the first attempts of its N draws (tn_variates)
+__host__ __device__ inline int e_sweep_extra(int N, int stage) { return (3 + (stage ? 3 * P_PRE : 0)) * N; }
+
 template <typename T>
-__global__ void k_e_sweep(Dev<T> d, int n_prev) {
+__global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
   extern __shared__ double sm[];
   const int K = d.K, N = d.N;
   const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Pn = sm;
   double* Mh = sm + K + (size_t)wid * 2 * K;
   double* Mv = Mh + K;
+  double* wx = sm + K + (size_t)WPB * 2 * K + (size_t)wid * e_sweep_extra(N, stage);
+  double* sE = wx;                       // [N] E[., g] before the sweep
+  double* sQ1 = sE + N;                  // [N] Lambda_e | Mu_e
+  double* sQ2 = sQ1 + N;                 // [N] Sigmasq_e
+  double* vZ = sQ2 + N;                  // [N][P_PRE] variates of the first attempts of every draw
+  double* vE = vZ + N * P_PRE;
+  double* vU = vE + N * P_PRE;
   const long long g = (long long)blockIdx.x * WPB + wid;
   const bool valid = g < d.G;
   const int iter = d.ctrl->iter, converged = d.ctrl->converged;
@@ -623,6 +646,17 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev) {
       Mh[k] = mh;
       Mv[k] = Mat(d, i);
     }
+    // everything the N sequential conditionals of this genome read besides Mhat: once, in parallel
+    for (int n = lane; n < N; n += 32) {
+      const long long idx = n + (long long)N * g;
+      sE[n] = (double)d.E[idx];
+      if (d.prior == PRIOR_EXPONENTIAL) { sQ1[n] = (double)d.Lambda_e[idx]; sQ2[n] = 0.0; }
+      else if (d.prior == PRIOR_TRUNCNORMAL) { sQ1[n] = (double)d.Mu_e[idx]; sQ2[n] = (double)d.Sigmasq_e[idx]; }
+    }
+    if (stage) for (int i = lane; i < N * P_PRE; i += 32) {
+      const int n = i / P_PRE, t = i - n * P_PRE;
+      tn_variates(make_stream(d.seed, iter, PUR_E, n + (long long)N * (d.g0 + g)), t, vZ[i], vE[i], vU[i]);
+    }
   }
   const double sg = (valid && normal) ? (double)d.sigmasq[g] : 0.0;
   for (int n = 0; n < N; ++n) {
@@ -633,7 +667,7 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev) {
     const int An = d.A[n];
     const long long idx = n + (long long)N * g;
     const long long c = n + (long long)N * (d.g0 + g);
-    const double Eold = (double)d.E[idx];
+    const double Eold = sE[n];
     const Stream st = make_stream(d.seed, iter, PUR_E, c);
     double x;
     if (An == 0 || d.nzP[n] == 0) {                               // R/sample_En.R:12,56
@@ -650,13 +684,14 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev) {
       num1 = warp_sum(num1); den = warp_sum(den);
       double mu, v;
       if (d.prior == PRIOR_EXPONENTIAL) {
-        mu = (num1 - (double)d.Lambda_e[idx]) / den; v = 1.0 / den;
+        mu = (num1 - sQ1[n]) / den; v = 1.0 / den;
       } else {
-        const double s2 = (double)d.Sigmasq_e[idx];
+        const double s2 = sQ2[n];
         den = den + 1.0 / s2;
-        mu = (num1 + (double)d.Mu_e[idx] / s2) / den; v = 1.0 / den;
+        mu = (num1 + sQ1[n] / s2) / den; v = 1.0 / den;
       }
-      x = truncnorm0_draw<double>(st, mu, sqrt(v));
+      x = stage ? truncnorm0_staged(st, mu, sqrt(v), vZ + n * P_PRE, vE + n * P_PRE, vU + n * P_PRE)
+                : truncnorm0_draw<double>(st, mu, sqrt(v));
     }
     x = (double)(T)x;
     double Enew = x;
