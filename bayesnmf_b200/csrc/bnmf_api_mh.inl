@@ -40,12 +40,15 @@ template <typename T> int Sampler<T>::mh_setup() {
   const size_t budget = 220 * 1024;
   // (the variates of the draws are staged only where that does not cost a resident warp: with long
   //  columns the sweep is bound by the reductions over K, not by the latency of a draw)
-  const long long w0 = ((long long)(budget / sizeof(double)) - K) / (2LL * K + e_sweep_extra(N, 0));
-  const long long w1 = ((long long)(budget / sizeof(double)) - K) / (2LL * K + e_sweep_extra(N, 1));
+  const long long ecols = e_sweep_cols(K, cfg.likelihood == BNMF_NORMAL);
+  const long long w0 = ((long long)(budget / sizeof(double)) - K) / (ecols + e_sweep_extra(N, 0));
+  const long long w1 = ((long long)(budget / sizeof(double)) - K) / (ecols + e_sweep_extra(N, 1));
   if (w0 < 1) return fail("k_e_sweep: K = %d does not fit one genome column in shared memory", K);
-  e_stage = std::min<long long>(8, w1) >= std::min<long long>(8, w0) ? 1 : 0;
-  e_wpb = (int)std::min<long long>(8, e_stage ? w1 : w0);
-  e_smem = ((size_t)(1 + 2 * e_wpb) * K + (size_t)e_wpb * e_sweep_extra(N, e_stage)) * sizeof(double);
+  const long long wmax = w0 <= 16 ? 16 : 8;                    // long columns: one block per SM with every warp that fits; short: 8-warp blocks
+  e_stage = std::min<long long>(wmax, w1) >= std::min<long long>(wmax, w0) ? 1 : 0;
+  e_wpb = (int)std::min<long long>(wmax, e_stage ? w1 : w0);
+  if ((long long)G < 148LL * 2 * e_wpb) e_wpb = (int)std::max<long long>(1, std::min<long long>(e_wpb, 8));   // small problems: more blocks
+  e_smem = ((size_t)K + (size_t)e_wpb * (ecols + e_sweep_extra(N, e_stage))) * sizeof(double);
   CK(cudaFuncSetAttribute(k_e_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
   // Row-resident P sweep: a cluster of CS blocks per mutation type keeps the row of M and Mhat in
   // shared memory.  CS is the cluster size that needs the fewest waves of clusters over the K rows

@@ -617,16 +617,22 @@ __global__ void __launch_bounds__(THREADS) k_p_rows(Dev<T> d, const T* __restric
 // doubles of shared memory per warp of k_e_sweep besides its two columns: the genome's column of E
 // and of the prior parameters, and the variates of the first attempts of its N draws (tn_variates)
 __host__ __device__ inline int e_sweep_extra(int N, int stage) { return (3 + (stage ? 3 * P_PRE : 0)) * N; }
+// doubles per warp for its two columns: Mhat (double) and the data (double for the Normal likelihood,
+// int32 counts for the Poisson one)
+__host__ __device__ inline int e_sweep_cols(int K, bool normal) { return K + (normal ? K : (K + 1) / 2); }
 
 template <typename T>
 __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
   extern __shared__ double sm[];
   const int K = d.K, N = d.N;
   const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool normal = d.likelihood == LIK_NORMAL;
+  const int cols = e_sweep_cols(K, normal);
   double* Pn = sm;
-  double* Mh = sm + K + (size_t)wid * 2 * K;
-  double* Mv = Mh + K;
-  double* wx = sm + K + (size_t)WPB * 2 * K + (size_t)wid * e_sweep_extra(N, stage);
+  double* Mh = sm + K + (size_t)wid * cols;
+  const double* MvD = Mh + K;                                   // data column: doubles (Normal) ...
+  const int32_t* MvI = reinterpret_cast<const int32_t*>(Mh + K);  // ... or counts (Poisson)
+  double* wx = sm + K + (size_t)WPB * cols + (size_t)wid * e_sweep_extra(N, stage);
   double* sE = wx;                       // [N] E[., g] before the sweep
   double* sQ1 = sE + N;                  // [N] Lambda_e | Mu_e
   double* sQ2 = sQ1 + N;                 // [N] Sigmasq_e
@@ -636,7 +642,6 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
   const long long g = (long long)blockIdx.x * WPB + wid;
   const bool valid = g < d.G;
   const int iter = d.ctrl->iter, converged = d.ctrl->converged;
-  const bool normal = d.likelihood == LIK_NORMAL;
   if (valid) {
     const double eprev = n_prev >= 0 ? (double)d.E[n_prev + (long long)N * g] : 0.0;
     for (int k = lane; k < K; k += 32) {
@@ -644,7 +649,7 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
       double mh = (double)d.Mhat[i];
       if (n_prev >= 0) mh = (double)(T)(mh + d.dvec[k] * eprev);
       Mh[k] = mh;
-      Mv[k] = Mat(d, i);
+      if (normal) const_cast<double*>(MvD)[k] = (double)d.Mr[i]; else const_cast<int32_t*>(MvI)[k] = d.Mi[i];
     }
     // everything the N sequential conditionals of this genome read besides Mhat: once, in parallel
     for (int n = lane; n < N; n += 32) {
@@ -678,7 +683,7 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
         const double mh = Mh[k], p = Pn[k];
         const double inv = 1.0 / (normal ? sg : mh);
         const double mh_no = mh - p * Eold;
-        num1 += p * ((Mv[k] - mh_no) * inv);
+        num1 += p * (((normal ? MvD[k] : (double)MvI[k]) - mh_no) * inv);
         den += (p * p) * inv;
       }
       num1 = warp_sum(num1); den = warp_sum(den);
@@ -701,7 +706,7 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
       } else {
         double D = 0.0;
         const double de = x - Eold;
-        for (int k = lane; k < K; k += 32) { const double mh = Mh[k]; D += mh_cell(Mv[k], mh, mh + Pn[k] * de); }
+        for (int k = lane; k < K; k += 32) { const double mh = Mh[k]; D += mh_cell(normal ? MvD[k] : (double)MvI[k], mh, mh + Pn[k] * de); }
         D = warp_sum(D);
         const double ratio = mh_ratio(D);
         if (lane == 0) d.E_acc[idx] = (T)ratio;
