@@ -50,11 +50,14 @@ def sharded_handle(M, N, dist, device=0, hyperprior_params=None, share_comm=None
     G = M.shape[1]
     lo, hi = shard_bounds(G, rank, world)
     h = Handle(M[:, lo:hi], N, device=device, g0=lo, G_total=G, **kw)
-    mean = global_mean(M[:, lo:hi], dist)
-    for name, value in fill_hyperprior_params(hyperprior_params, kw.get("prior", "gamma"), mean, N).items():
-        if np.ndim(value) == 2 and name.endswith("_e"):
-            value = np.asarray(value)[:, lo:hi]
-        h.set_hyper(name, value)
+    if world > 1 or hyperprior_params:
+        # (a single unsharded handle without user values keeps the defaults bnmf_create installed from
+        #  the mean of its own -- that is, of all -- columns: R/setup.R:123-181)
+        mean = global_mean(M[:, lo:hi], dist)
+        for name, value in fill_hyperprior_params(hyperprior_params, kw.get("prior", "gamma"), mean, N).items():
+            if np.ndim(value) == 2 and name.endswith("_e"):
+                value = np.asarray(value)[:, lo:hi]
+            h.set_hyper(name, value)
     if world > 1 and share_comm is not None:
         h.comm_share(share_comm)
     elif world > 1:
