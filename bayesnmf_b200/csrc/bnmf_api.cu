@@ -671,6 +671,8 @@ struct Sampler : bnmf_handle {
   // row-resident P sweep (k_p_rows): cluster size, genomes per block, threads, shared memory; 0 = not used
   int pr_cs = 0, pr_gslice = 0, pr_threads = 0; size_t pr_smem = 0; long long pr_Gp = 0; T* Et = nullptr;
   int p_rows_launch();
+  double* gram_part = nullptr; double* gram_buf = nullptr; int gram_chunks = 0;   // Normal likelihood: Gram-matrix P sweep
+  int p_gram_launch();
   double* asum = nullptr; double sig_alpha = 3.0, sig_beta = 3.0;
 
   // End of an iteration.  Sharded runs sum everything the next iteration (SP, rowSums(E):

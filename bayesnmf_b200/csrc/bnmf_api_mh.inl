@@ -50,6 +50,12 @@ template <typename T> int Sampler<T>::mh_setup() {
   if ((long long)G < 148LL * 2 * e_wpb) e_wpb = (int)std::max<long long>(1, std::min<long long>(e_wpb, 8));   // small problems: more blocks
   e_smem = ((size_t)K + (size_t)e_wpb * (ecols + e_sweep_extra(N, e_stage))) * sizeof(double);
   CK(cudaFuncSetAttribute(k_e_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
+  // Normal likelihood: the P sweep through two Gram matrices (k_gram_part ...); BNMF_GRAM=0 turns it off
+  if (cfg.likelihood == BNMF_NORMAL && !(getenv("BNMF_GRAM") && atoi(getenv("BNMF_GRAM")) == 0)) {
+    gram_chunks = (int)((G + GRAM_GC - 1) / GRAM_GC);
+    const long long len = (long long)K * N + (long long)N * N;
+    if (dalloc(&gram_part, (long long)gram_chunks * len) || dalloc(&gram_buf, len)) return 1;
+  }
   // Row-resident P sweep: a cluster of CS blocks per mutation type keeps the row of M and Mhat in
   // shared memory.  CS is the cluster size that needs the fewest waves of clusters over the K rows
   // (ties: the smaller slice per block); BNMF_P_ROWS=0 keeps the pass-per-signature kernels.
@@ -91,6 +97,20 @@ template <typename T> int Sampler<T>::mh_setup() {
       if (dalloc(&Et, (long long)N * pr_Gp)) return 1;
     }
   }
+  return 0;
+}
+
+// P sweep of the Normal likelihood: Gram matrices, the chain per mutation type, Mhat rebuilt
+template <typename T> int Sampler<T>::p_gram_launch() {
+  const int K = cfg.K, N = cfg.N;
+  const long long len = (long long)K * N + (long long)N * N, KG = (long long)K * cfg.G;
+  const dim3 grid((unsigned)gram_chunks, (unsigned)((K + GRAM_KT - 1) / GRAM_KT));
+  k_gram_part<T><<<grid, GRAM_KT, (size_t)2 * N * GRAM_GC * sizeof(double), stream>>>(d, gram_part);
+  k_gram_fold<<<blocks(len, 128), 128, 0, stream>>>(gram_part, gram_buf, len, gram_chunks);
+  constexpr int PW = 4;
+  k_p_gram<T, PW><<<(K + PW - 1) / PW, 32 * PW, (size_t)PW * N * (1 + 3 * P_PRE) * sizeof(double), stream>>>(d, gram_buf);
+  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d);
+  launches += 4;
   return 0;
 }
 
@@ -154,7 +174,8 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
     const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
     const size_t psm = (size_t)p_kx * p_gy * 2 * sizeof(double);
     const int dblocks = (K + 3) / 4;       // k_p_draw / k_p_accept: a warp per mutation type
-    if (pr_cs) { if (p_rows_launch()) return 1; }
+    if (gram_buf) { if (p_gram_launch()) return 1; }
+    else if (pr_cs) { if (p_rows_launch()) return 1; }
     else for (int n = 0; n < N; ++n) {
       k_p_pass1<T><<<pgrid, pblock, psm, stream>>>(d, n, n ? n - 1 : -1);
       k_p_draw<T><<<dblocks, 128, 0, stream>>>(d, n);
@@ -165,7 +186,7 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
         launches += 2;
       }
     }
-    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, pr_cs ? -1 : N - 1, e_stage); ++launches;
+    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, (pr_cs || gram_buf) ? -1 : N - 1, e_stage); ++launches;
     int pending = -1;
     if (cfg.learning_rank) { if (rank_sweep_kernels(&pending)) return 1; }
     k_final<T><<<col_blocks, 256, 0, stream>>>(d, pending, 0); ++launches;

@@ -609,6 +609,130 @@ __global__ void __launch_bounds__(THREADS) k_p_rows(Dev<T> d, const T* __restric
 }
 
 // ------------------------------------------------------------------------------
+// P sweep of the Normal likelihood through two Gram matrices.  There the variance of a cell does
+// not depend on the mutation type (s[k,g] = sigmasq_g, R/sample_Pn.R:140-143), so with
+// W = diag(1 / sigmasq) the sums of get_mu_sigmasq_Pn_normal (R/sample_Pn.R:132-187) factor:
+//     num1[k] = (M W E')[k,n] - sum_{m != n} P[k,m] A_m (E W E')[m,n],     den = A_n (E W E')[n,n]
+// (P[k,m] the current value: already redrawn for m < n).  One pass over M and E per iteration
+// (k_gram_part + k_gram_fold, fixed summation order) replaces a pass per signature; the N
+// conditionals of a mutation type are then a chain over two small matrices (k_p_gram, a warp per
+// mutation type), and Mhat is rebuilt once (k_mhat_full).  Algebraically the reference's sums,
+// not their summation order.
+// ------------------------------------------------------------------------------
+constexpr int GRAM_GC = 32;      // genomes per block of k_gram_part
+constexpr int GRAM_KT = 128;     // mutation types per block (one per thread)
+// part[chunk][K*N + N*N]: A1 = M W E' (K x N, k fastest) then A2 = E W E' (N x N)
+template <typename T>
+__global__ void __launch_bounds__(GRAM_KT) k_gram_part(Dev<T> d, double* __restrict__ part) {
+  extern __shared__ double gsm[];
+  const int K = d.K, N = d.N;
+  double* Ew = gsm;                    // [N][GC]  E[n,g] / sigmasq_g
+  double* Es = gsm + N * GRAM_GC;      // [N][GC]  E[n,g]
+  const long long g0 = (long long)blockIdx.x * GRAM_GC;
+  const int ng = (int)min((long long)GRAM_GC, (long long)d.G - g0);
+  for (int i = threadIdx.x; i < N * GRAM_GC; i += GRAM_KT) {
+    const int j = i / N, n = i - j * N;            // n fastest: coalesced reads of E
+    double e = 0.0, w = 0.0;
+    if (j < ng) { e = (double)d.E[n + (long long)N * (g0 + j)]; w = 1.0 / (double)d.sigmasq[g0 + j]; }
+    Es[n * GRAM_GC + j] = e;
+    Ew[n * GRAM_GC + j] = e * w;
+  }
+  __syncthreads();
+  double* out = part + (long long)blockIdx.x * ((long long)K * N + (long long)N * N);
+  const int k = blockIdx.y * GRAM_KT + threadIdx.x;
+  if (k < K) {
+    double mrow[GRAM_GC];
+#pragma unroll
+    for (int j = 0; j < GRAM_GC; ++j) mrow[j] = j < ng ? (double)d.Mr[k + (long long)K * (g0 + j)] : 0.0;
+    for (int n = 0; n < N; ++n) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < GRAM_GC; ++j) acc += mrow[j] * Ew[n * GRAM_GC + j];
+      out[k + (long long)K * n] = acc;
+    }
+  }
+  if (blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < N * N; i += GRAM_KT) {
+      const int m = i % N, n = i / N;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < GRAM_GC; ++j) acc += Ew[m * GRAM_GC + j] * Es[n * GRAM_GC + j];
+      out[(long long)K * N + i] = acc;
+    }
+  }
+}
+// gram[i] = sum over chunks of part[chunk][i], in chunk order
+__global__ void k_gram_fold(const double* __restrict__ part, double* __restrict__ gram, long long len, int n_chunks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;      // four interleaved running sums, combined in a fixed order
+  int c = 0;
+  for (; c + 3 < n_chunks; c += 4) {
+    a0 += part[(long long)c * len + i]; a1 += part[(long long)(c + 1) * len + i];
+    a2 += part[(long long)(c + 2) * len + i]; a3 += part[(long long)(c + 3) * len + i];
+  }
+  for (; c < n_chunks; ++c) a0 += part[(long long)c * len + i];
+  gram[i] = (a0 + a1) + (a2 + a3);
+}
+// the N conditionals of mutation type k, one warp per k
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_p_gram(Dev<T> d, const double* __restrict__ gram) {
+  extern __shared__ double psm[];
+  const int K = d.K, N = d.N;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int k = blockIdx.x * WARPS + wid;
+  if (k >= K) return;
+  double* wbase = psm + (size_t)wid * (N * (1 + 3 * P_PRE));
+  double* Prow = wbase;                // [N] current row of P (A folded in below)
+  double* vZ = Prow + N;               // [N][P_PRE] variates of the first attempts of the N draws
+  double* vE = vZ + N * P_PRE;
+  double* vU = vE + N * P_PRE;
+  const double* A1 = gram;
+  const double* A2 = gram + (long long)K * N;
+  const int iter = d.ctrl->iter;
+  for (int n = lane; n < N; n += 32) Prow[n] = (double)d.P[k + (long long)K * n];
+  for (int i = lane; i < N * P_PRE; i += 32) {
+    const int n = i / P_PRE, t = i - n * P_PRE;
+    tn_variates(make_stream(d.seed, iter, PUR_P, k + (long long)K * n), t, vZ[i], vE[i], vU[i]);
+  }
+  __syncwarp();
+  for (int n = 0; n < N; ++n) {
+    const int An = d.A[n];
+    const long long c = k + (long long)K * n;
+    const bool zero_row = d.nzE[((iter - 1) & 1) * N + n] == 0;   // all(E[n, ] == 0), R/sample_Pn.R:56
+    const Stream st = make_stream(d.seed, iter, PUR_P, c);
+    double x;
+    if (An == 0 || zero_row) {
+      x = prior_draw(d, st, 0, c);
+    } else {
+      double s = 0.0;
+      for (int m = lane; m < N; m += 32)
+        if (m != n && d.A[m]) s += Prow[m] * A2[m + (long long)N * n];
+      s = warp_sum(s);
+      const double num1 = A1[c] - s;
+      double den = A2[n + (long long)N * n];
+      double mu, v;
+      if (d.prior == PRIOR_EXPONENTIAL) {
+        mu = (num1 - (double)d.Lambda_p[c]) / den; v = 1.0 / den;
+      } else {
+        const double sg = (double)d.Sigmasq_p[c];
+        den = den + 1.0 / sg;
+        mu = (num1 + (double)d.Mu_p[c] / sg) / den; v = 1.0 / den;
+      }
+      x = truncnorm0_staged(st, mu, sqrt(v), vZ + n * P_PRE, vE + n * P_PRE, vU + n * P_PRE);
+    }
+    x = (double)(T)x;
+    __syncwarp();
+    if (lane == 0) {
+      Prow[n] = x;
+      d.P[c] = (T)x;
+      if (x != 0.0) atomicOr(&d.nzP[n], 1);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------
 // k_e_sweep: all N updates of E[., g] for one genome per warp.  The genome's column of M
 // and of the running Mhat stay in shared memory for the whole sweep; column n of P is
 // staged once per block and shared by its warps; the reductions over k are warp

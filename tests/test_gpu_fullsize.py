@@ -71,31 +71,40 @@ def test_c3_full_size_iterations_conserve_counts(built_lib):
 
 
 @pytest.mark.parametrize("lik,prior,MH", [("poisson", "exponential", True), ("normal", "truncnormal", False)])
-def test_p_sweep_rows_equal_passes(built_lib, lik, prior, MH):
-    """k_p_rows (a cluster of blocks per mutation type, rows resident in shared memory) and the
-    pass-per-signature kernels implement the same conditionals with different summation orders:
-    states agree to 1e-9 relative over several iterations, before and after `converged`.
-    G is large enough that a row spans several blocks of a cluster."""
+def test_p_sweep_implementations_agree(built_lib, lik, prior, MH):
+    """The P sweep exists three times: k_p_rows (a cluster of blocks per mutation type, rows resident
+    in shared memory), the pass-per-signature kernels, and -- Normal likelihood -- the Gram-matrix
+    form.  Same conditionals, different summation orders (Gram: a different but algebraically equal
+    expression): states agree to 1e-9 (1e-7 for Gram) relative over several iterations, before and
+    after `converged`.  G is large enough that a row spans several blocks of a cluster."""
     from bayesnmf_b200 import Handle
     K, G, N = 6, 40_000, 4
     M, _, _ = synth_counts(K, G, N, 600.0, seed=2)
     if lik == "normal":
         M = M + np.random.default_rng(5).normal(0.0, 1.0, M.shape)
-    res = []
-    for rows in ("1", "0"):
-        os.environ["BNMF_P_ROWS"] = rows
+    variants = [("rows", {"BNMF_GRAM": "0"}), ("passes", {"BNMF_GRAM": "0", "BNMF_P_ROWS": "0"})]
+    if lik == "normal":
+        variants.append(("gram", {}))
+    res = {}
+    for name, env in variants:
+        os.environ.update(env)
         try:
             h = Handle(M, N, likelihood=lik, prior=prior, MH=MH, seed=4)
         finally:
-            os.environ.pop("BNMF_P_ROWS", None)
+            for k in env:
+                os.environ.pop(k, None)
         h.init_from_prior()
         h.step(3)
         out = h.step(2, converged=True) if MH else h.step(2)
-        res.append((h.get_state("P"), h.get_state("E"), h.get_state("Mhat"), out["metrics"][-1], h.timing()["launches"]))
+        res[name] = (h.get_state("P"), h.get_state("E"), h.get_state("Mhat"), out["metrics"][-1], h.timing()["launches"])
         h.close()
-    (P1, E1, H1, m1, l1), (P0, E0, H0, m0, l0) = res
-    assert l1 < l0                                             # the cluster kernel replaced 2N (4N) launches
-    np.testing.assert_allclose(P1, P0, rtol=1e-9, atol=1e-300)
-    np.testing.assert_allclose(E1, E0, rtol=1e-9, atol=1e-300)
-    np.testing.assert_allclose(H1, H0, rtol=1e-9, atol=1e-12)
-    np.testing.assert_allclose(m1, m0, rtol=1e-9, atol=1e-9, equal_nan=True)
+    assert res["rows"][4] < res["passes"][4]                   # the cluster kernel replaced 2N (4N) launches
+    for name, rtol in (("rows", 1e-9), ("gram", 1e-7)):
+        if name not in res:
+            continue
+        P1, E1, H1, m1, _ = res[name]
+        P0, E0, H0, m0, _ = res["passes"]
+        np.testing.assert_allclose(P1, P0, rtol=rtol, atol=1e-300, err_msg=name)
+        np.testing.assert_allclose(E1, E0, rtol=rtol, atol=1e-300, err_msg=name)
+        np.testing.assert_allclose(H1, H0, rtol=rtol, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(m1, m0, rtol=rtol, atol=1e-7, equal_nan=True, err_msg=name)
