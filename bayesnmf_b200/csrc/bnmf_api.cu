@@ -667,7 +667,7 @@ struct Sampler : bnmf_handle {
   int rank_sweep_kernels(int* pending);
   int refresh_metrics_only();
   bool sweep_model = false; int h_converged = 0;
-  int p_kx = 32, p_gy = 8, p_ktiles = 1, col_blocks = 1, e_wpb = 8, e_stage = 0; size_t e_smem = 0;
+  int p_kx = 32, p_gy = 8, p_ktiles = 1, col_blocks = 1, e_wpb = 8, e_stage = 0, e_lpg = 32, e_slots = 8; size_t e_smem = 0;
   // row-resident P sweep (k_p_rows): cluster size, genomes per block, threads, shared memory; 0 = not used
   int pr_cs = 0, pr_gslice = 0, pr_threads = 0; size_t pr_smem = 0; long long pr_Gp = 0; T* Et = nullptr;
   int p_rows_launch();

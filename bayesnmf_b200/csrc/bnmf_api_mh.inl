@@ -36,20 +36,30 @@ template <typename T> int Sampler<T>::mh_setup() {
   d.n_gchunks = (int)((G + d.gchunk - 1) / d.gchunk);
   col_blocks = (int)((G + 7) / 8);
   if (dalloc(&d.ppart, (long long)d.n_gchunks * K * 2) || dalloc(&d.apart, 2LL * col_blocks)) return 1;
-  // E sweep: warps per block limited by the shared-memory columns
-  const size_t budget = 220 * 1024;
-  // (the variates of the draws are staged only where that does not cost a resident warp: with long
-  //  columns the sweep is bound by the reductions over K, not by the latency of a draw)
-  const long long ecols = e_sweep_cols(K, cfg.likelihood == BNMF_NORMAL);
-  const long long w0 = ((long long)(budget / sizeof(double)) - K) / (ecols + e_sweep_extra(N, 0));
-  const long long w1 = ((long long)(budget / sizeof(double)) - K) / (ecols + e_sweep_extra(N, 1));
-  if (w0 < 1) return fail("k_e_sweep: K = %d does not fit one genome column in shared memory", K);
-  const long long wmax = w0 <= 16 ? 16 : 8;                    // long columns: one block per SM with every warp that fits; short: 8-warp blocks
-  e_stage = std::min<long long>(wmax, w1) >= std::min<long long>(wmax, w0) ? 1 : 0;
-  e_wpb = (int)std::min<long long>(wmax, e_stage ? w1 : w0);
-  if ((long long)G < 148LL * 2 * e_wpb) e_wpb = (int)std::max<long long>(1, std::min<long long>(e_wpb, 8));   // small problems: more blocks
-  e_smem = ((size_t)K + (size_t)e_wpb * (ecols + e_sweep_extra(N, e_stage))) * sizeof(double);
-  CK(cudaFuncSetAttribute(k_e_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
+  // E sweep: lanes per genome by the column length, genome slots per block by the shared memory
+  e_lpg = K <= 128 ? 8 : K <= 256 ? 16 : 32;
+  if (G < 148LL * 32) e_lpg = 32;                              // few genomes: every one its own warp, the GPU has room
+  {
+    const int gpw = 32 / e_lpg;
+    const size_t budget = 220 * 1024;
+    const long long ecols = e_sweep_cols(K, cfg.likelihood == BNMF_NORMAL);
+    // (the variates of the draws are staged only where that does not cost a resident warp: with long
+    //  columns the sweep is bound by the reductions over K, not by the latency of a draw)
+    const long long s0 = ((long long)(budget / sizeof(double)) - K) / (ecols + e_sweep_extra(N, 0));
+    const long long s1 = ((long long)(budget / sizeof(double)) - K) / (ecols + e_sweep_extra(N, 1));
+    if (s0 < 1) return fail("k_e_sweep: K = %d does not fit one genome column in shared memory", K);
+    const long long wmax = s0 / gpw <= 16 ? 16 : 8;            // long columns: one block per SM with every warp that fits; short: 8-warp blocks
+    const long long w0 = std::max<long long>(1, std::min<long long>(wmax, s0 / gpw)), w1 = std::min<long long>(wmax, s1 / gpw);
+    e_stage = w1 >= w0 ? 1 : 0;
+    e_wpb = (int)(e_stage ? w1 : w0);
+    while (e_wpb > 1 && (G + (long long)e_wpb * gpw - 1) / ((long long)e_wpb * gpw) < 2 * 148) e_wpb >>= 1;   // small problems: more, smaller blocks
+    if (s0 < gpw) { e_lpg = 32; e_wpb = (int)std::min<long long>(16, s0); e_stage = 0; }   // (not even one warp of short-column slots fits)
+    e_slots = e_wpb * (32 / e_lpg);
+    e_smem = ((size_t)K + (size_t)e_slots * (ecols + e_sweep_extra(N, e_stage))) * sizeof(double);
+    CK(cudaFuncSetAttribute(k_e_sweep<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
+    CK(cudaFuncSetAttribute(k_e_sweep<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
+    CK(cudaFuncSetAttribute(k_e_sweep<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem));
+  }
   // Normal likelihood: the P sweep through two Gram matrices (k_gram_part ...); BNMF_GRAM=0 turns it off
   if (cfg.likelihood == BNMF_NORMAL && !(getenv("BNMF_GRAM") && atoi(getenv("BNMF_GRAM")) == 0)) {
     gram_chunks = (int)((G + GRAM_GC - 1) / GRAM_GC);
@@ -106,7 +116,7 @@ template <typename T> int Sampler<T>::p_gram_launch() {
   const long long len = (long long)K * N + (long long)N * N, KG = (long long)K * cfg.G;
   const dim3 grid((unsigned)gram_chunks, (unsigned)((K + GRAM_KT - 1) / GRAM_KT));
   k_gram_part<T><<<grid, GRAM_KT, (size_t)2 * N * GRAM_GC * sizeof(double), stream>>>(d, gram_part);
-  k_gram_fold<<<blocks(len, 128), 128, 0, stream>>>(gram_part, gram_buf, len, gram_chunks);
+  k_gram_fold<<<blocks(len * 32, 256), 256, 0, stream>>>(gram_part, gram_buf, len, gram_chunks);
   constexpr int PW = 4;
   k_p_gram<T, PW><<<(K + PW - 1) / PW, 32 * PW, (size_t)PW * N * (1 + 3 * P_PRE) * sizeof(double), stream>>>(d, gram_buf);
   k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d);
@@ -169,8 +179,8 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
   } else {
     k_hyper<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0);
     k_hyper<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1);
-    k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d);
-    launches += 3;
+    launches += 2;
+    if (!gram_buf) { k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); ++launches; }   // (the Gram-matrix P sweep rebuilds Mhat after itself)
     const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
     const size_t psm = (size_t)p_kx * p_gy * 2 * sizeof(double);
     const int dblocks = (K + 3) / 4;       // k_p_draw / k_p_accept: a warp per mutation type
@@ -186,7 +196,14 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
         launches += 2;
       }
     }
-    k_e_sweep<T><<<(unsigned)((G + e_wpb - 1) / e_wpb), 32 * e_wpb, e_smem, stream>>>(d, (pr_cs || gram_buf) ? -1 : N - 1, e_stage); ++launches;
+    {
+      const unsigned eg = (unsigned)((G + e_slots - 1) / e_slots);
+      const int np = (pr_cs || gram_buf) ? -1 : N - 1;
+      if (e_lpg == 8) k_e_sweep<T, 8><<<eg, 32 * e_wpb, e_smem, stream>>>(d, np, e_stage);
+      else if (e_lpg == 16) k_e_sweep<T, 16><<<eg, 32 * e_wpb, e_smem, stream>>>(d, np, e_stage);
+      else k_e_sweep<T, 32><<<eg, 32 * e_wpb, e_smem, stream>>>(d, np, e_stage);
+      ++launches;
+    }
     int pending = -1;
     if (cfg.learning_rank) { if (rank_sweep_kernels(&pending)) return 1; }
     k_final<T><<<col_blocks, 256, 0, stream>>>(d, pending, 0); ++launches;

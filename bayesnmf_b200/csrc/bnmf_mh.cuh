@@ -661,18 +661,15 @@ __global__ void __launch_bounds__(GRAM_KT) k_gram_part(Dev<T> d, double* __restr
     }
   }
 }
-// gram[i] = sum over chunks of part[chunk][i], in chunk order
+// gram[i] = sum over chunks of part[chunk][i]: a warp per element, lanes stride over the chunks, fixed butterfly
 __global__ void k_gram_fold(const double* __restrict__ part, double* __restrict__ gram, long long len, int n_chunks) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= len) return;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;      // four interleaved running sums, combined in a fixed order
-  int c = 0;
-  for (; c + 3 < n_chunks; c += 4) {
-    a0 += part[(long long)c * len + i]; a1 += part[(long long)(c + 1) * len + i];
-    a2 += part[(long long)(c + 2) * len + i]; a3 += part[(long long)(c + 3) * len + i];
-  }
-  for (; c < n_chunks; ++c) a0 += part[(long long)c * len + i];
-  gram[i] = (a0 + a1) + (a2 + a3);
+  double a = 0.0;
+  for (int c = lane; c < n_chunks; c += 32) a += part[(long long)c * len + i];
+  a = warp_sum(a);
+  if (lane == 0) gram[i] = a;
 }
 // the N conditionals of mutation type k, one warp per k
 template <typename T, int WARPS>
@@ -745,111 +742,126 @@ __host__ __device__ inline int e_sweep_extra(int N, int stage) { return (3 + (st
 // int32 counts for the Poisson one)
 __host__ __device__ inline int e_sweep_cols(int K, bool normal) { return K + (normal ? K : (K + 1) / 2); }
 
-template <typename T>
+// sum over the LPG consecutive lanes of a sub-group (LPG = 8, 16 or 32), fixed butterfly order
+template <int LPG> __device__ __forceinline__ double seg_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int o = LPG >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+// LPG lanes per genome: with short columns (K <= 128) a warp carries 4 (2) genomes, each on its own
+// 8 (16) lanes, so that the scalar part of a conditional is not repeated by 32 lanes.
+template <typename T, int LPG>
 __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
   extern __shared__ double sm[];
   const int K = d.K, N = d.N;
-  const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int GPW = 32 / LPG;                               // genomes per warp
+  const int sub = lane / LPG, l = lane - sub * LPG;
+  const int SPB = (blockDim.x >> 5) * GPW;                    // genome slots per block
+  const int slot = wid * GPW + sub;
   const bool normal = d.likelihood == LIK_NORMAL;
   const int cols = e_sweep_cols(K, normal);
   double* Pn = sm;
-  double* Mh = sm + K + (size_t)wid * cols;
-  const double* MvD = Mh + K;                                   // data column: doubles (Normal) ...
-  const int32_t* MvI = reinterpret_cast<const int32_t*>(Mh + K);  // ... or counts (Poisson)
-  double* wx = sm + K + (size_t)WPB * cols + (size_t)wid * e_sweep_extra(N, stage);
+  double* Mh = sm + K + (size_t)slot * cols;
+  double* MvD = Mh + K;                                       // data column: doubles (Normal) ...
+  int32_t* MvI = reinterpret_cast<int32_t*>(Mh + K);         // ... or counts (Poisson)
+  double* wx = sm + K + (size_t)SPB * cols + (size_t)slot * e_sweep_extra(N, stage);
   double* sE = wx;                       // [N] E[., g] before the sweep
   double* sQ1 = sE + N;                  // [N] Lambda_e | Mu_e
   double* sQ2 = sQ1 + N;                 // [N] Sigmasq_e
   double* vZ = sQ2 + N;                  // [N][P_PRE] variates of the first attempts of every draw
   double* vE = vZ + N * P_PRE;
   double* vU = vE + N * P_PRE;
-  const long long g = (long long)blockIdx.x * WPB + wid;
+  const long long g = (long long)blockIdx.x * SPB + slot;
   const bool valid = g < d.G;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);   // whole sub-groups are valid or not
   const int iter = d.ctrl->iter, converged = d.ctrl->converged;
   if (valid) {
     const double eprev = n_prev >= 0 ? (double)d.E[n_prev + (long long)N * g] : 0.0;
-    for (int k = lane; k < K; k += 32) {
+    for (int k = l; k < K; k += LPG) {
       const long long i = k + (long long)K * g;
       double mh = (double)d.Mhat[i];
       if (n_prev >= 0) mh = (double)(T)(mh + d.dvec[k] * eprev);
       Mh[k] = mh;
-      if (normal) const_cast<double*>(MvD)[k] = (double)d.Mr[i]; else const_cast<int32_t*>(MvI)[k] = d.Mi[i];
+      if (normal) MvD[k] = (double)d.Mr[i]; else MvI[k] = d.Mi[i];
     }
     // everything the N sequential conditionals of this genome read besides Mhat: once, in parallel
-    for (int n = lane; n < N; n += 32) {
+    for (int n = l; n < N; n += LPG) {
       const long long idx = n + (long long)N * g;
       sE[n] = (double)d.E[idx];
       if (d.prior == PRIOR_EXPONENTIAL) { sQ1[n] = (double)d.Lambda_e[idx]; sQ2[n] = 0.0; }
       else if (d.prior == PRIOR_TRUNCNORMAL) { sQ1[n] = (double)d.Mu_e[idx]; sQ2[n] = (double)d.Sigmasq_e[idx]; }
     }
-    if (stage) for (int i = lane; i < N * P_PRE; i += 32) {
+    if (stage) for (int i = l; i < N * P_PRE; i += LPG) {
       const int n = i / P_PRE, t = i - n * P_PRE;
       tn_variates(make_stream(d.seed, iter, PUR_E, n + (long long)N * (d.g0 + g)), t, vZ[i], vE[i], vU[i]);
     }
   }
-  const double sg = (valid && normal) ? (double)d.sigmasq[g] : 0.0;
+  const double inv_sg = (valid && normal) ? 1.0 / (double)d.sigmasq[g] : 0.0;
   for (int n = 0; n < N; ++n) {
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x) Pn[k] = (double)d.P[k + (long long)K * n];
     __syncthreads();
-    if (!valid) continue;
-    const int An = d.A[n];
-    const long long idx = n + (long long)N * g;
-    const long long c = n + (long long)N * (d.g0 + g);
-    const double Eold = sE[n];
-    const Stream st = make_stream(d.seed, iter, PUR_E, c);
-    double x;
-    if (An == 0 || d.nzP[n] == 0) {                               // R/sample_En.R:12,56
-      x = prior_draw(d, st, 1, idx);
-    } else {
-      double num1 = 0.0, den = 0.0;
-      for (int k = lane; k < K; k += 32) {
-        const double mh = Mh[k], p = Pn[k];
-        const double inv = 1.0 / (normal ? sg : mh);
-        const double mh_no = mh - p * Eold;
-        num1 += p * (((normal ? MvD[k] : (double)MvI[k]) - mh_no) * inv);
-        den += (p * p) * inv;
-      }
-      num1 = warp_sum(num1); den = warp_sum(den);
-      double mu, v;
-      if (d.prior == PRIOR_EXPONENTIAL) {
-        mu = (num1 - sQ1[n]) / den; v = 1.0 / den;
+    if (valid) {
+      const int An = d.A[n];
+      const long long idx = n + (long long)N * g;
+      const long long c = n + (long long)N * (d.g0 + g);
+      const double Eold = sE[n];
+      const Stream st = make_stream(d.seed, iter, PUR_E, c);
+      double x;
+      if (An == 0 || d.nzP[n] == 0) {                               // R/sample_En.R:12,56
+        x = prior_draw(d, st, 1, idx);
       } else {
-        const double s2 = sQ2[n];
-        den = den + 1.0 / s2;
-        mu = (num1 + sQ1[n] / s2) / den; v = 1.0 / den;
+        double num1 = 0.0, den = 0.0;
+        for (int k = l; k < K; k += LPG) {
+          const double mh = Mh[k], p = Pn[k];
+          const double inv = normal ? inv_sg : 1.0 / mh;
+          const double mh_no = mh - p * Eold;
+          num1 += p * (((normal ? MvD[k] : (double)MvI[k]) - mh_no) * inv);
+          den += (p * p) * inv;
+        }
+        num1 = seg_sum<LPG>(num1, vmask); den = seg_sum<LPG>(den, vmask);
+        double mu, v;
+        if (d.prior == PRIOR_EXPONENTIAL) {
+          mu = (num1 - sQ1[n]) / den; v = 1.0 / den;
+        } else {
+          const double s2 = sQ2[n];
+          den = den + 1.0 / s2;
+          mu = (num1 + sQ1[n] / s2) / den; v = 1.0 / den;
+        }
+        x = stage ? truncnorm0_staged(st, mu, sqrt(v), vZ + n * P_PRE, vE + n * P_PRE, vU + n * P_PRE)
+                  : truncnorm0_draw<double>(st, mu, sqrt(v));
       }
-      x = stage ? truncnorm0_staged(st, mu, sqrt(v), vZ + n * P_PRE, vE + n * P_PRE, vU + n * P_PRE)
-                : truncnorm0_draw<double>(st, mu, sqrt(v));
-    }
-    x = (double)(T)x;
-    double Enew = x;
-    if (d.MH && An != 0) {
-      if (!converged) {
-        if (lane == 0) d.E_acc[idx] = (T)1;                         // R/sample_En.R:198-201
-      } else {
-        double D = 0.0;
-        const double de = x - Eold;
-        for (int k = lane; k < K; k += 32) { const double mh = Mh[k]; D += mh_cell(normal ? MvD[k] : (double)MvI[k], mh, mh + Pn[k] * de); }
-        D = warp_sum(D);
-        const double ratio = mh_ratio(D);
-        if (lane == 0) d.E_acc[idx] = (T)ratio;
-        const double u = u01<double>(make_stream(d.seed, iter, PUR_MH_E, c).at(0).x);
-        Enew = u < ratio ? x : Eold;
+      x = (double)(T)x;
+      double Enew = x;
+      if (d.MH && An != 0) {
+        if (!converged) {
+          if (l == 0) d.E_acc[idx] = (T)1;                          // R/sample_En.R:198-201
+        } else {
+          double D = 0.0;
+          const double de = x - Eold;
+          for (int k = l; k < K; k += LPG) { const double mh = Mh[k]; D += mh_cell(normal ? MvD[k] : (double)MvI[k], mh, mh + Pn[k] * de); }
+          D = seg_sum<LPG>(D, vmask);
+          const double ratio = mh_ratio(D);
+          if (l == 0) d.E_acc[idx] = (T)ratio;
+          const double u = u01<double>(make_stream(d.seed, iter, PUR_MH_E, c).at(0).x);
+          Enew = u < ratio ? x : Eold;
+        }
       }
-    }
-    if (An != 0 && Enew != Eold) {
-      const double de = Enew - Eold;
-      for (int k = lane; k < K; k += 32) Mh[k] = (double)(T)(Mh[k] + Pn[k] * de);
-    }
-    if (lane == 0) {
-      d.E[idx] = (T)Enew;
-      if (Enew != 0.0) atomicOr(&d.nzE[(iter & 1) * N + n], 1);
+      if (An != 0 && Enew != Eold) {
+        const double de = Enew - Eold;
+        for (int k = l; k < K; k += LPG) Mh[k] = (double)(T)(Mh[k] + Pn[k] * de);
+      }
+      if (l == 0) {
+        d.E[idx] = (T)Enew;
+        if (Enew != 0.0) atomicOr(&d.nzE[(iter & 1) * N + n], 1);
+      }
     }
     __syncwarp();
   }
   if (valid)
-    for (int k = lane; k < K; k += 32) d.Mhat[k + (long long)K * g] = (T)Mh[k];
+    for (int k = l; k < K; k += LPG) d.Mhat[k + (long long)K * g] = (T)Mh[k];
 }
 
 // ------------------------------------------------------------------------------
