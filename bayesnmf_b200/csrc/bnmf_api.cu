@@ -318,7 +318,7 @@ struct Sampler : bnmf_handle {
     d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, ET);
     if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + 2 * N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
         dalloc(&d.red, PC_COLS) || dalloc(&work_ctr, n_ktiles + 8) || dalloc(&nanflags, 5 * N)) return 1;
-    if (dalloc(&d.ctrl, 1) || dalloc(&red_slices, RED_BLOCKS * PC_COLS) || dalloc(&red_ticket, 1)) return 1;
+    if (dalloc(&d.ctrl, 1) || dalloc(&red_slices, RED_BLOCKS * PC_COLS) || dalloc(&red_ticket, 2)) return 1;
     d.metrics_cap = 256;
     if (dalloc(&d.metrics, (long long)d.metrics_cap * MC_COLS)) return 1;
     CK(cudaMallocHost((void**)&h_metrics, (size_t)d.metrics_cap * MC_COLS * sizeof(double)));

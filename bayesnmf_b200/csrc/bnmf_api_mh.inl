@@ -142,7 +142,11 @@ template <typename T> int Sampler<T>::rank_sweep_kernels(int* pending) {
   const int N = cfg.N;
   k_r<T><<<1, 32, 0, stream>>>(d); ++launches;
   for (int n = 0; n < N; ++n) {
-    k_a_pass<T><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1); ++launches;
+    if (world <= 1) {     // nothing to exchange: the last block of the pass reduces and draws
+      k_a_pass<T, 1><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1, red_ticket + 1); ++launches;
+      continue;
+    }
+    k_a_pass<T, 0><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1, nullptr); ++launches;
     k_a_reduce<T><<<1, 256, 0, stream>>>(d, col_blocks, asum); ++launches;
     if (allreduce_buf(asum, 2, NCCL_FLOAT64, NCCL_SUM)) return 1;
     k_a_draw<T, 256><<<1, 256, 0, stream>>>(d, n, asum); ++launches;

@@ -898,10 +898,15 @@ __global__ void k_r(Dev<T> d) {
   *d.R = r < N ? r : N;
 }
 
+template <typename T, int THREADS>
+__device__ __forceinline__ void a_draw_block(const Dev<T>& d, int n, double l0, double l1);
+
 // k_a_pass: one streaming pass giving the log-likelihood with A_n = 0 and with A_n = 1
 // (the two get_loglik calls of R/sample_params.R:115-116); a warp per genome column.
-template <typename T>
-__global__ void k_a_pass(Dev<T> d, int n, int n_prev) {
+// FUSE = 1 (unsharded runs): the block that finishes last folds the per-block partials in a fixed
+// order and draws A_n itself -- one launch per signature instead of three (k_a_reduce, k_a_draw).
+template <typename T, int FUSE>
+__global__ void __launch_bounds__(256) k_a_pass(Dev<T> d, int n, int n_prev, unsigned* ticket) {
   __shared__ double s0[32], s1[32];
   const int K = d.K, N = d.N;
   const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -935,14 +940,33 @@ __global__ void k_a_pass(Dev<T> d, int n, int n_prev) {
     for (int w = 0; w < WPB; ++w) { a += s0[w]; b += s1[w]; }
     d.apart[2 * (long long)blockIdx.x] = a; d.apart[2 * (long long)blockIdx.x + 1] = b;
   }
+  if (FUSE) {
+    __shared__ bool last;
+    __shared__ double scratch[8];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    const volatile double* ap = d.apart;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) { a += ap[2 * (long long)i]; b += ap[2 * (long long)i + 1]; }
+    a = block_sum<256>(a, scratch);
+    b = block_sum<256>(b, scratch);
+    __shared__ double tot[2];
+    if (threadIdx.x == 0) { tot[0] = a; tot[1] = b; *ticket = 0u; }
+    __syncthreads();
+    a_draw_block<T, 256>(d, n, tot[0], tot[1]);
+  }
 }
 
 // k_a_draw: A_n ~ Bernoulli(p), SBFI / BFI (R/sample_params.R:118-165); one block.
+// (a device function: also the tail of k_a_pass<.., FUSE = 1>)
 template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_a_draw(Dev<T> d, int n, const double* lsum) {
+__device__ __forceinline__ void a_draw_block(const Dev<T>& d, int n, double l0, double l1) {
   __shared__ int s_delta;
   const int K = d.K, N = d.N;
-  double l0 = lsum[0], l1 = lsum[1];
   if (threadIdx.x == 0) {
     const int iter = d.ctrl->iter;
     if (d.likelihood == LIK_POISSON) { l0 += d.ll_const; l1 += d.ll_const; }
@@ -976,6 +1000,10 @@ __global__ void __launch_bounds__(THREADS) k_a_draw(Dev<T> d, int n, const doubl
   __syncthreads();
   const double dl = (double)s_delta;
   for (int k = threadIdx.x; k < K; k += THREADS) d.dvec[k] = dl * (double)d.P[k + (long long)K * n];
+}
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_a_draw(Dev<T> d, int n, const double* lsum) {
+  a_draw_block<T, THREADS>(d, n, lsum[0], lsum[1]);
 }
 
 // ------------------------------------------------------------------------------
