@@ -153,7 +153,8 @@ class Handle:
         n = int(np.prod(shp))
         out = np.empty(n, dtype=np.float64)
         self._ck(lib().bnmf_get_state(self._h, name.encode(), _dp(out), n))
-        return out.reshape(shp[::-1]).T.copy() if len(shp) == 2 else out
+        # (the library hands back R's layout: a column-major view, no transposing copy)
+        return out.reshape(shp, order="F") if len(shp) == 2 else out
 
     def set_temperature_schedule(self, temps):
         t = np.ascontiguousarray(np.asarray(temps, dtype=np.float64))
@@ -190,7 +191,8 @@ class Handle:
         n = int(np.prod(shp))
         out = np.empty(n)
         self._ck(lib().bnmf_get_sample(self._h, name.encode(), int(ago), _dp(out), n))
-        return out.reshape(shp[::-1]).T.copy() if len(shp) == 2 else out
+        # (the library hands back R's layout: a column-major view, no transposing copy)
+        return out.reshape(shp, order="F") if len(shp) == 2 else out
 
     def get_map(self, n_samples):
         P = np.empty(self.K * self.N); E = np.empty(self.N * self.G); A = np.empty(self.N)

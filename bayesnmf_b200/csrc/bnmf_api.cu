@@ -12,6 +12,7 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -147,6 +148,11 @@ template <typename T> static __global__ void k_hist_copy(Dev<T> d, T* P_hist, in
 constexpr int ET = 512;   // threads per block of k_eside
 enum StType { ST_T, ST_I32, ST_U64 };
 struct StEntry { void* p; long long len; StType ty; };
+
+// process-wide pinned staging buffer for the upload of count matrices (bnmf_create)
+static std::mutex g_pin_mutex;
+static void* g_pin = nullptr;
+static size_t g_pin_bytes = 0;
 
 template <typename T>
 struct Sampler : bnmf_handle {
@@ -339,9 +345,22 @@ struct Sampler : bnmf_handle {
     std::vector<long double> ch_sum((size_t)n_ch, 0.0L);
     std::vector<long long> ch_bad((size_t)n_ch, -1);             // first offending cell of a chunk
     std::vector<int> ch_why((size_t)n_ch, 0);
-    std::vector<int32_t> h_mi;
+    // counts go through a process-wide pinned staging buffer (kept between handles: a fresh 38 MB
+    // vector costs more in page faults than the whole pass over the data)
     const bool pois = cfg.likelihood == BNMF_POISSON;
-    if (pois) h_mi.resize((size_t)KG);
+    std::unique_lock<std::mutex> pin_lock(g_pin_mutex, std::defer_lock);
+    int32_t* h_mi = nullptr;
+    if (pois) {
+      pin_lock.lock();
+      const size_t need = (size_t)KG * sizeof(int32_t);
+      if (g_pin_bytes < need) {
+        if (g_pin) cudaFreeHost(g_pin);
+        g_pin = nullptr; g_pin_bytes = 0;
+        CK(cudaMallocHost(&g_pin, need));
+        g_pin_bytes = need;
+      }
+      h_mi = static_cast<int32_t*>(g_pin);
+    }
     {
       auto work = [&](long long c) {
         const long long g_lo = c * CH, g_hi = std::min(G, g_lo + CH);
@@ -390,7 +409,7 @@ struct Sampler : bnmf_handle {
     if (pois) {
       int32_t* mi; if (dalloc(&mi, KG)) return 1;
       lap("alloc counts");
-      CK(cudaMemcpyAsync(mi, h_mi.data(), (size_t)KG * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(mi, h_mi, (size_t)KG * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
       lap("memcpy counts");
       d.Mi = mi;
       const int nb = 296;
@@ -402,6 +421,7 @@ struct Sampler : bnmf_handle {
       double a = 0, b = 0;
       for (int i = 0; i < nb; ++i) { a += hc[2 * i]; b += hc[2 * i + 1]; }
       d.ll_const = a; d.kl_const = b;
+      pin_lock.unlock();                       // (the stream was synchronised above: the upload is done)
     } else {
       if (ensure_stage(KG)) return 1;
       CK(cudaMemcpyAsync(stage, data, (size_t)KG * sizeof(double), cudaMemcpyHostToDevice, stream));
