@@ -66,6 +66,7 @@ def lib():
     L.bnmf_ring_count.argtypes = [vp, ctypes.POINTER(i32)]
     L.bnmf_get_sample.argtypes = [vp, cp, i32, dp, i64]
     L.bnmf_get_map.argtypes = [vp, i32, dp, dp, dp, ctypes.POINTER(i32)]
+    L.bnmf_get_credible_intervals.argtypes = [vp, i32, ctypes.c_double, ctypes.c_double, dp, dp, dp, dp, ctypes.POINTER(i32)]
     L.bnmf_comm_unique_id.argtypes = [ctypes.c_char_p]
     L.bnmf_comm_init.argtypes = [vp, ctypes.c_char_p, i32, i32]
     L.bnmf_comm_share.argtypes = [vp, vp]
@@ -78,7 +79,7 @@ def lib():
 
 EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
            "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
-           "bnmf_step", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_comm_unique_id",
+           "bnmf_step", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_get_credible_intervals", "bnmf_comm_unique_id",
            "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z"]
 
 
@@ -193,6 +194,17 @@ class Handle:
         self._ck(lib().bnmf_get_sample(self._h, name.encode(), int(ago), _dp(out), n))
         # (the library hands back R's layout: a column-major view, no transposing copy)
         return out.reshape(shp, order="F") if len(shp) == 2 else out
+
+    def get_credible_intervals(self, n_samples, lower_p=0.025, upper_p=0.975):
+        """(P_lower, P_upper, E_lower, E_upper, n_match): element-wise quantiles over the samples that
+        match the modal A, computed on the device ring (R/utils.R:264-287)."""
+        KN, NG = self.K * self.N, self.N * self.G
+        Pl, Ph, El, Eh = np.empty(KN), np.empty(KN), np.empty(NG), np.empty(NG)
+        nm = ctypes.c_int32()
+        self._ck(lib().bnmf_get_credible_intervals(self._h, int(n_samples), float(lower_p), float(upper_p),
+                                                   _dp(Pl), _dp(Ph), _dp(El), _dp(Eh), ctypes.byref(nm)))
+        f = lambda a, r, c: a.reshape((r, c), order="F")
+        return f(Pl, self.K, self.N), f(Ph, self.K, self.N), f(El, self.N, self.G), f(Eh, self.N, self.G), nm.value
 
     def get_map(self, n_samples):
         P = np.empty(self.K * self.N); E = np.empty(self.N * self.G); A = np.empty(self.N)

@@ -84,6 +84,7 @@ struct bnmf_handle {
   virtual int ring_count(int* c) = 0;
   virtual int get_sample(const char* name, int ago, double* out, int64_t len) = 0;
   virtual int get_map(int n_samples, double* P, double* E, double* A, int* n_match) = 0;
+  virtual int get_ci(int n_samples, double plo, double phi, double* P_lo, double* P_hi, double* E_lo, double* E_hi, int* n_match) = 0;
   virtual int comm_init(const char* id, int rank, int world) = 0;
   virtual int comm_share(bnmf_handle* src) = 0;
   std::shared_ptr<CommBox> commbox; int world = 1, rank = 0;
@@ -872,6 +873,8 @@ struct Sampler : bnmf_handle {
     return fail("bnmf_get_sample: the ring holds P, E and A (got '%s')", name);
   }
   int get_map(int n_samples, double* P, double* E, double* A, int* n_match) override;
+  int get_ci(int n_samples, double plo, double phi, double* P_lo, double* P_hi, double* E_lo, double* E_hi, int* n_match) override;
+  int map_slots(int n_samples, std::vector<int>& match, std::string& mode);
 
   int set_l2_flush(size_t bytes) override {
     CK(cudaSetDevice(cfg.device));
@@ -998,6 +1001,9 @@ int bnmf_step(bnmf_handle* h, int32_t n, int32_t conv, double* m, double* P, dou
 int bnmf_ring_count(bnmf_handle* h, int32_t* c) { NEED(h); return h->ring_count(c); }
 int bnmf_get_sample(bnmf_handle* h, const char* name, int32_t ago, double* out, int64_t len) { NEED(h); return h->get_sample(name, ago, out, len); }
 int bnmf_get_map(bnmf_handle* h, int32_t n, double* P, double* E, double* A, int32_t* nm) { NEED(h); return h->get_map(n, P, E, A, nm); }
+int bnmf_get_credible_intervals(bnmf_handle* h, int32_t n, double plo, double phi, double* P_lo, double* P_hi, double* E_lo, double* E_hi, int32_t* nm) {
+  NEED(h); return h->get_ci(n, plo, phi, P_lo, P_hi, E_lo, E_hi, nm);
+}
 int bnmf_comm_unique_id(char* id128) {
   if (load_nccl()) return 1;
   int r = g_nccl.GetUniqueId(id128);

@@ -34,14 +34,14 @@ template <typename T> static __global__ void k_map_mean_E(Dev<T> d, const int* s
   out[i] = acc / (double)n_match;
 }
 
-template <typename T> int Sampler<T>::get_map(int n_samples, double* P_map, double* E_map, double* A_map, int* n_match_out) {
-  CK(cudaSetDevice(cfg.device));
+// slots of the newest n_samples ring samples whose A equals the modal A (oldest first), and that A
+template <typename T> int Sampler<T>::map_slots(int n_samples, std::vector<int>& match, std::string& mode) {
   if (d.ring_cap <= 0) return fail("bnmf_get_map: the handle was created with ring_cap = 0");
   Ctrl hc; CK(cudaMemcpyAsync(&hc, d.ctrl, sizeof(hc), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   if (n_samples < 1 || n_samples > hc.ring_count)
     return fail("bnmf_get_map: n_samples = %d outside the %d samples held", n_samples, hc.ring_count);
-  const int N = cfg.N, K = cfg.K; const long long KN = (long long)K * N, NG = (long long)N * cfg.G;
+  const int N = cfg.N;
   std::vector<int32_t> ringA((size_t)d.ring_cap * N);
   CK(cudaMemcpyAsync(ringA.data(), d.ring_A, sizeof(int32_t) * ringA.size(), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
@@ -59,10 +59,18 @@ template <typename T> int Sampler<T>::get_map(int n_samples, double* P_map, doub
   // that order among ties, so the modal pattern is the most frequent, smallest string
   std::map<std::string, int> cnt;
   for (auto& s : key) cnt[s] += 1;
-  std::string mode; int best = -1;
+  int best = -1;
   for (auto& kv : cnt) if (kv.second > best) { best = kv.second; mode = kv.first; }
-  std::vector<int> match;
+  match.clear();
   for (int j = 0; j < n_samples; ++j) if (key[j] == mode) match.push_back(slot[j]);
+  return 0;
+}
+
+template <typename T> int Sampler<T>::get_map(int n_samples, double* P_map, double* E_map, double* A_map, int* n_match_out) {
+  CK(cudaSetDevice(cfg.device));
+  std::vector<int> match; std::string mode;
+  if (map_slots(n_samples, match, mode)) return 1;
+  const int N = cfg.N, K = cfg.K; const long long KN = (long long)K * N, NG = (long long)N * cfg.G;
   const int nm = (int)match.size();
   int* dslots; double* colsum; double* outP; double* outE;
   CK(cudaMalloc((void**)&dslots, sizeof(int) * nm));
@@ -79,6 +87,96 @@ template <typename T> int Sampler<T>::get_map(int n_samples, double* P_map, doub
   CK(cudaGetLastError());
   cudaFree(dslots); cudaFree(colsum); cudaFree(outP); cudaFree(outE);
   if (A_map) for (int n = 0; n < N; ++n) A_map[n] = mode[n] == '1' ? 1.0 : 0.0;
+  if (n_match_out) *n_match_out = nm;
+  return 0;
+}
+
+// Credible intervals of get_MAP_ (R/utils.R:264-287): element-wise quantiles (R's default, type 7:
+// x[j] + (h - j)(x[j+1] - x[j]), h = (n - 1) p) of the renormalised P and E over the samples that
+// match the modal A.  A block takes CI_EPB consecutive elements: every matching sample contributes
+// one contiguous segment (coalesced), a warp sorts the values of one element in shared memory
+// (bitonic, padded with +inf to a power of two) and picks the two quantiles.  The E samples
+// (N x G each, up to MAP_over of them) never leave HBM.
+constexpr int CI_EPB = 8;
+template <typename T> static __global__ void __launch_bounds__(32 * CI_EPB)
+k_ci(Dev<T> d, const int* slots, int nm, int NS, const double* colsum, int side, double plo, double phi,
+     double* out_lo, double* out_hi) {
+  extern __shared__ double cv[];                       // [CI_EPB][NS]
+  const long long len = side == 0 ? (long long)d.K * d.N : (long long)d.N * d.G;
+  const T* ring = side == 0 ? d.ring_P : d.ring_E;
+  const long long i0 = (long long)blockIdx.x * CI_EPB;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < CI_EPB * NS; t += blockDim.x) {
+    const int e = t % CI_EPB, s = t / CI_EPB;
+    const long long i = i0 + e;
+    double v = INFINITY;
+    if (s < nm && i < len) {
+      const int n = side == 0 ? (int)(i / d.K) : (int)(i % d.N);
+      const double cs = colsum[(long long)s * d.N + n];
+      const double x = (double)ring[(long long)slots[s] * len + i];
+      v = side == 0 ? x / cs : x * cs;                 // renormalize, R/helpers.R:35-49
+      if (v != v) v = INFINITY;                        // (0 / 0 columns sort last, as NaN would in R's quantile with na.rm)
+    }
+    cv[e * NS + s] = v;
+  }
+  __syncthreads();
+  double* x = cv + wid * NS;
+  for (int k = 2; k <= NS; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int idx = lane; idx < NS; idx += 32) {
+        const int partner = idx ^ j;
+        if (partner > idx) {
+          const double a = x[idx], b = x[partner];
+          const bool up = (idx & k) == 0;
+          if ((a > b) == up) { x[idx] = b; x[partner] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  const long long i = i0 + wid;
+  if (lane < 2 && i < len) {
+    const double p = lane == 0 ? plo : phi;
+    const double h = (double)(nm - 1) * p;
+    int j = (int)floor(h);
+    if (j > nm - 1) j = nm - 1;
+    const double g = h - (double)j;
+    const double a = x[j], b = x[j + 1 < nm ? j + 1 : nm - 1];
+    const double q = a + g * (b - a);
+    (lane == 0 ? out_lo : out_hi)[i] = q;
+  }
+}
+
+template <typename T> int Sampler<T>::get_ci(int n_samples, double plo, double phi, double* P_lo, double* P_hi,
+                                             double* E_lo, double* E_hi, int* n_match_out) {
+  CK(cudaSetDevice(cfg.device));
+  if (!(plo >= 0.0 && phi <= 1.0 && plo <= phi)) return fail("bnmf_get_credible_intervals: need 0 <= lower <= upper <= 1");
+  std::vector<int> match; std::string mode;
+  if (map_slots(n_samples, match, mode)) return 1;
+  const int N = cfg.N, K = cfg.K; const long long KN = (long long)K * N, NG = (long long)N * cfg.G;
+  const int nm = (int)match.size();
+  int NS = 2; while (NS < nm) NS <<= 1;
+  const size_t smem = (size_t)CI_EPB * NS * sizeof(double);
+  if (smem > (size_t)200 * 1024) return fail("bnmf_get_credible_intervals: %d matching samples do not fit the sort buffer", nm);
+  CK(cudaFuncSetAttribute(k_ci<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int* dslots; double* colsum; double* lo; double* hi;
+  CK(cudaMalloc((void**)&dslots, sizeof(int) * nm));
+  CK(cudaMalloc((void**)&colsum, sizeof(double) * (size_t)nm * N));
+  CK(cudaMalloc((void**)&lo, sizeof(double) * std::max(KN, NG)));
+  CK(cudaMalloc((void**)&hi, sizeof(double) * std::max(KN, NG)));
+  CK(cudaMemcpyAsync(dslots, match.data(), sizeof(int) * nm, cudaMemcpyHostToDevice, stream));
+  k_map_colsum<T><<<dim3(N, nm), 128, 0, stream>>>(d, dslots, colsum);
+  for (int side = 0; side < 2; ++side) {
+    double* o_lo = side == 0 ? P_lo : E_lo; double* o_hi = side == 0 ? P_hi : E_hi;
+    if (!o_lo && !o_hi) continue;
+    const long long len = side == 0 ? KN : NG;
+    k_ci<T><<<(unsigned)((len + CI_EPB - 1) / CI_EPB), 32 * CI_EPB, smem, stream>>>(d, dslots, nm, NS, colsum, side, plo, phi, lo, hi);
+    if (o_lo) CK(cudaMemcpyAsync(o_lo, lo, sizeof(double) * len, cudaMemcpyDeviceToHost, stream));
+    if (o_hi) CK(cudaMemcpyAsync(o_hi, hi, sizeof(double) * len, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  CK(cudaGetLastError());
+  cudaFree(dslots); cudaFree(colsum); cudaFree(lo); cudaFree(hi);
   if (n_match_out) *n_match_out = nm;
   return 0;
 }

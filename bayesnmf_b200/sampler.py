@@ -170,17 +170,12 @@ class bayesNMF_sampler:
         self.MAP = dict(P=P_map[:, keep_sigs], A=A_map[keep_sigs].reshape(1, -1), E=E_map[keep_sigs, :], idx=idx,
                         A_counts=top[:5], keep_sigs=keep_sigs)
         if final or self.credible_intervals is not None:                 # :264-287, quantile type 7
-            probs = [0.5 - credible_interval / 2, 0.5 + credible_interval / 2]
-            sel = [i for i, k in enumerate(keys) if k == mode_key]
-            Ps = np.stack([self.samples["P"][-n_s:][i] for i in sel])
-            cs = Ps.sum(axis=1)                                          # colSums(P) per sample
-            with np.errstate(divide="ignore", invalid="ignore"):
-                Pr = (Ps / cs[:, None, :])[:, :, keep_sigs]
-            Es = np.stack([self.sample_E(n_s - 1 - i) for i in sel])
-            Er = (Es * cs[:, :, None])[:, keep_sigs, :]
-            qP = np.quantile(Pr, probs, axis=0)
-            qE = np.quantile(Er, probs, axis=0)
-            self.credible_intervals = dict(P=dict(lower=qP[0], upper=qP[1]), E=dict(lower=qE[0], upper=qE[1]))
+            # element-wise quantiles over the matching samples, on the device ring: the E samples
+            # (N x G each) never cross PCIe
+            Pl, Ph, El, Eh, nm = self._h.get_credible_intervals(n_s, 0.5 - credible_interval / 2, 0.5 + credible_interval / 2)
+            assert nm == n_match
+            self.credible_intervals = dict(P=dict(lower=Pl[:, keep_sigs], upper=Ph[:, keep_sigs]),
+                                           E=dict(lower=El[keep_sigs, :], upper=Eh[keep_sigs, :]))
 
     def _update_MAP_metrics(self, final=False):
         """update_MAP_metrics_ + compute_metrics_(MAP = TRUE) (R/utils.R:356-397, :412-455)."""

@@ -124,6 +124,13 @@ int bnmf_get_sample(bnmf_handle* h, const char* name, int32_t ago, double* out, 
 int bnmf_get_map(bnmf_handle* h, int32_t n_samples, double* P_map, double* E_map,
                  double* A_map, int32_t* n_match);
 
+/* The credible intervals of get_MAP_ (R/utils.R:264-287: apply(arr, c(1, 2), quantile, probs)) on
+ * the device: over the same matching samples, element-wise quantiles (type 7) `lower_p` and
+ * `upper_p` of the renormalised P (K x N) and E (N x G).  Any output may be NULL. */
+int bnmf_get_credible_intervals(bnmf_handle* h, int32_t n_samples, double lower_p, double upper_p,
+                                double* P_lower, double* P_upper, double* E_lower, double* E_upper,
+                                int32_t* n_match);
+
 /* Cross-shard reduction for genome-sharded runs (one process per GPU): each rank
  * creates its shard handle, rank 0 makes an id, every rank joins.  Afterwards
  * bnmf_step sums SP, rowSums(E) and the metric partials over ranks with NCCL. */

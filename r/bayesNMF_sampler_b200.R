@@ -91,5 +91,11 @@ b200_get_MAP <- function(self, private, n_samples) {
   r <- .Call("R_bnmf_get_map", private$h, as.integer(n_samples), self$dims$K, self$dims$N, self$dims$G)
   list(P = r[[1]], E = r[[2]], A = matrix(r[[3]], nrow = 1), n_match = r[[4]])
 }
+# credible_intervals of get_MAP_ (R/utils.R:264-287): quantile(type 7) over the same samples, on the device
+b200_credible_intervals <- function(self, private, n_samples, credible_interval = 0.95) {
+  probs <- c(0.5 - credible_interval / 2, 0.5 + credible_interval / 2)
+  r <- .Call("R_bnmf_get_ci", private$h, as.integer(n_samples), probs, self$dims$K, self$dims$N, self$dims$G)
+  list(P = list(lower = r[[1]], upper = r[[2]]), E = list(lower = r[[3]], upper = r[[4]]))
+}
 b200_sample_E <- function(self, private, ago = 0L)
   .Call("R_bnmf_get_sample", private$h, "E", as.integer(ago), self$dims$N, self$dims$G)

@@ -127,6 +127,22 @@ SEXP R_bnmf_get_map(SEXP p, SEXP n_samples, SEXP K, SEXP N, SEXP G) {
   CK(rc);
   return out;
 }
+/* credible_intervals of get_MAP_, R/utils.R:264-287, on the device ring:
+ * list(P_lower, P_upper, E_lower, E_upper, n_match) */
+SEXP R_bnmf_get_ci(SEXP p, SEXP n_samples, SEXP probs, SEXP K, SEXP N, SEXP G) {
+  int k = Rf_asInteger(K), nn = Rf_asInteger(N), g = Rf_asInteger(G);
+  SEXP Pl = PROTECT(Rf_allocMatrix(REALSXP, k, nn)), Ph = PROTECT(Rf_allocMatrix(REALSXP, k, nn));
+  SEXP El = PROTECT(Rf_allocMatrix(REALSXP, nn, g)), Eh = PROTECT(Rf_allocMatrix(REALSXP, nn, g));
+  int32_t n_match = 0;
+  int rc = bnmf_get_credible_intervals(H(p), Rf_asInteger(n_samples), REAL(probs)[0], REAL(probs)[1],
+                                       REAL(Pl), REAL(Ph), REAL(El), REAL(Eh), &n_match);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 5));
+  SET_VECTOR_ELT(out, 0, Pl); SET_VECTOR_ELT(out, 1, Ph); SET_VECTOR_ELT(out, 2, El); SET_VECTOR_ELT(out, 3, Eh);
+  SET_VECTOR_ELT(out, 4, Rf_ScalarInteger(n_match));
+  UNPROTECT(5);
+  CK(rc);
+  return out;
+}
 /* samples$E[[i]] on demand (update_list ring, R/helpers.R:111-119); ago = 0 is the newest */
 SEXP R_bnmf_get_sample(SEXP p, SEXP name, SEXP ago, SEXP nrow, SEXP ncol) {
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(nrow), Rf_asInteger(ncol)));
@@ -171,6 +187,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bnmf_set_state", (DL_FUNC)&R_bnmf_set_state, 3},     {"R_bnmf_get_state", (DL_FUNC)&R_bnmf_get_state, 4},
   {"R_bnmf_set_temps", (DL_FUNC)&R_bnmf_set_temps, 2},     {"R_bnmf_init", (DL_FUNC)&R_bnmf_init, 3},
   {"R_bnmf_step", (DL_FUNC)&R_bnmf_step, 5},               {"R_bnmf_get_map", (DL_FUNC)&R_bnmf_get_map, 5},
+  {"R_bnmf_get_ci", (DL_FUNC)&R_bnmf_get_ci, 6},
   {"R_bnmf_get_sample", (DL_FUNC)&R_bnmf_get_sample, 5},   {"R_bnmf_ring_count", (DL_FUNC)&R_bnmf_ring_count, 1},
   {"R_bnmf_comm_unique_id", (DL_FUNC)&R_bnmf_comm_unique_id, 0}, {"R_bnmf_comm_init", (DL_FUNC)&R_bnmf_comm_init, 4},
   {"R_bnmf_comm_share", (DL_FUNC)&R_bnmf_comm_share, 2},   {"R_bnmf_timing", (DL_FUNC)&R_bnmf_timing, 1},

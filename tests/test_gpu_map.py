@@ -39,6 +39,19 @@ def test_ring_and_map(built_lib, lik, prior, MH, learn):
         np.testing.assert_allclose(P_map.sum(axis=0), 1.0, rtol=1e-12)     # renormalised signatures
     with pytest.raises(BnmfError):
         h.get_map(cap + 1)
+    # credible intervals (R/utils.R:264-287): quantile type 7 of the renormalised matching samples
+    for n_s, (lo, hi) in ((cap, (0.025, 0.975)), (10, (0.1, 0.5)), (1, (0.025, 0.975))):
+        _, _, oA, idx = get_MAP(Ps[-n_s:], Es[-n_s:], As[-n_s:])
+        sel = [i for i in range(n_s) if np.array_equal(As[-n_s:][i], oA)]
+        Pm = np.stack([Ps[-n_s:][i] for i in sel]); cs = Pm.sum(axis=1)
+        Pr = Pm / cs[:, None, :]
+        Er = np.stack([Es[-n_s:][i] for i in sel]) * cs[:, :, None]
+        Pl, Ph, El, Eh, nm = h.get_credible_intervals(n_s, lo, hi)
+        assert nm == len(sel)
+        np.testing.assert_allclose(Pl, np.quantile(Pr, lo, axis=0), rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(Ph, np.quantile(Pr, hi, axis=0), rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(El, np.quantile(Er, lo, axis=0), rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(Eh, np.quantile(Er, hi, axis=0), rtol=1e-12, atol=1e-300)
 
 
 def test_map_without_ring_fails(built_lib):
