@@ -63,6 +63,7 @@ def lib():
     L.bnmf_set_temperature_schedule.argtypes = [vp, dp, i64]
     L.bnmf_init_from_prior.argtypes = [vp, u32, u32, dp]
     L.bnmf_step.argtypes = [vp, i32, i32, dp, dp, dp]
+    L.bnmf_run.argtypes = [vp, ctypes.c_void_p, i32, dp, i64, dp, i64, ctypes.c_void_p]
     L.bnmf_ring_count.argtypes = [vp, ctypes.POINTER(i32)]
     L.bnmf_get_sample.argtypes = [vp, cp, i32, dp, i64]
     L.bnmf_get_map.argtypes = [vp, i32, dp, dp, dp, ctypes.POINTER(i32)]
@@ -77,9 +78,28 @@ def lib():
     return L
 
 
+class ConvergenceControl(ctypes.Structure):
+    """bnmf_convergence_control of include/bnmf.h."""
+    _fields_ = [("MAP_over", ctypes.c_int32), ("MAP_every", ctypes.c_int32), ("tol", ctypes.c_double),
+                ("Ninarow_nochange", ctypes.c_int32), ("Ninarow_nobest", ctypes.c_int32), ("miniters", ctypes.c_int32),
+                ("maxiters", ctypes.c_int32), ("metric", ctypes.c_int32)]
+
+
+class RunResult(ctypes.Structure):
+    """bnmf_run_result of include/bnmf.h."""
+    _fields_ = [("iter", ctypes.c_int32), ("converged", ctypes.c_int32), ("converged_iter", ctypes.c_int32), ("why", ctypes.c_int32),
+                ("best_iter", ctypes.c_int32), ("n_checks", ctypes.c_int32), ("n_rows", ctypes.c_int32),
+                ("inarow_no_change", ctypes.c_int32), ("inarow_no_best", ctypes.c_int32), ("inarow_na", ctypes.c_int32),
+                ("best_MAP_metric", ctypes.c_double), ("prev_MAP_metric", ctypes.c_double)]
+
+
+RUN_METRICS = {"logposterior": 0, "loglikelihood": 1, "BIC": 2}
+RUN_WHY = {0: None, 1: "no change", 2: "no best", 3: "max iters"}
+MAP_METRIC_NAMES = ["iter", "loglikelihood", "logposterior", "n_params", "BIC", "rank", "MAP_A_counts", "mean_temp"]
+
 EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
            "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
-           "bnmf_step", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_get_credible_intervals", "bnmf_comm_unique_id",
+           "bnmf_step", "bnmf_run", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_get_credible_intervals", "bnmf_comm_unique_id",
            "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z"]
 
 
@@ -194,6 +214,24 @@ class Handle:
         self._ck(lib().bnmf_get_sample(self._h, name.encode(), int(ago), _dp(out), n))
         # (the library hands back R's layout: a column-major view, no transposing copy)
         return out.reshape(shp, order="F") if len(shp) == 2 else out
+
+    def run(self, convergence_control, post_warmup=0):
+        """run_gibbs_sampler behind the ABI (bnmf_run): advances until convergence (+ post_warmup
+        iterations with the real MH accept step).  Returns dict(result fields, metrics, MAP_metrics)."""
+        cc = convergence_control
+        c = ConvergenceControl(MAP_over=cc["MAP_over"], MAP_every=cc["MAP_every"], tol=cc["tol"],
+                               Ninarow_nochange=cc["Ninarow_nochange"], Ninarow_nobest=cc["Ninarow_nobest"],
+                               miniters=cc["miniters"], maxiters=cc["maxiters"], metric=RUN_METRICS[cc.get("metric", "logposterior")])
+        rows_cap = cc["maxiters"] + int(post_warmup) + 8
+        checks_cap = rows_cap // max(cc["MAP_every"], 1) + 8
+        met = np.empty((rows_cap, MC_COLS)); mm = np.empty((checks_cap, len(MAP_METRIC_NAMES)))
+        res = RunResult()
+        self._ck(lib().bnmf_run(self._h, ctypes.byref(c), int(post_warmup), _dp(met), rows_cap, _dp(mm), checks_cap, ctypes.byref(res)))
+        out = {f: getattr(res, f) for f, _ in RunResult._fields_}
+        out["why"] = RUN_WHY[res.why]
+        out["metrics"] = met[:res.n_rows]
+        out["MAP_metrics"] = [dict(zip(MAP_METRIC_NAMES, r)) for r in mm[:res.n_checks]]
+        return out
 
     def get_credible_intervals(self, n_samples, lower_p=0.025, upper_p=0.975):
         """(P_lower, P_upper, E_lower, E_upper, n_match): element-wise quantiles over the samples that

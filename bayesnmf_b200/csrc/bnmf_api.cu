@@ -81,6 +81,8 @@ struct bnmf_handle {
   virtual int set_temps(const double* t, int64_t n) = 0;
   virtual int init_from_prior(uint32_t have, uint32_t have_prior, double* row) = 0;
   virtual int step(int n_iters, int converged, double* metrics, double* P_out, double* A_out) = 0;
+  virtual int run(const bnmf_convergence_control* cc, int post_warmup, double* metrics_out, int64_t rows_cap,
+                  double* map_out, int64_t checks_cap, bnmf_run_result* res) = 0;
   virtual int ring_count(int* c) = 0;
   virtual int get_sample(const char* name, int ago, double* out, int64_t len) = 0;
   virtual int get_map(int n_samples, double* P, double* E, double* A, int* n_match) = 0;
@@ -185,6 +187,8 @@ struct Sampler : bnmf_handle {
   bool time_z = true;
   double last_total_ms = 0, last_z_ms = 0; int64_t last_launches = 0;
   bool have_temps = false;
+  std::vector<double> h_temps;                             // host copy of the temperature schedule (bnmf_run)
+  std::vector<double> h_rows;                              // every sample_metrics row so far, MC_COLS each (bnmf_run's windows)
 
   ~Sampler() override {
     cudaSetDevice(cfg.device);
@@ -575,6 +579,7 @@ struct Sampler : bnmf_handle {
     CK(cudaMemcpyAsync(p, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
     d.temps = p; d.n_temps = (int)n; have_temps = true;
+    h_temps.assign(t, t + n);
     drop_graph();
     return 0;
   }
@@ -755,6 +760,7 @@ struct Sampler : bnmf_handle {
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
     if (row) memcpy(row, h_metrics, sizeof(double) * MC_COLS);
+    h_rows.assign(h_metrics, h_metrics + MC_COLS);
     return 0;
   }
   int init_sigmasq_prior();
@@ -839,6 +845,8 @@ struct Sampler : bnmf_handle {
       CK(cudaStreamSynchronize(stream));
       CK(cudaGetLastError());
       if (metrics) memcpy(metrics + (long long)done * MC_COLS, h_metrics, sizeof(double) * MC_COLS * chunk);
+      if (h_rows.size() > (size_t)MC_COLS * 2000000) h_rows.erase(h_rows.begin(), h_rows.begin() + (long long)MC_COLS * 1000000);
+      h_rows.insert(h_rows.end(), h_metrics, h_metrics + (size_t)MC_COLS * chunk);
       if (P_out) { if (dev_to_host(P_hist, ST_T, (long long)chunk * KN, P_out + (long long)done * KN)) return 1; }
       if (A_out) { if (dev_to_host(A_hist, ST_I32, (long long)chunk * N, A_out + (long long)done * N)) return 1; }
       if (timez) for (int i = 0; i < chunk; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, zev[2 * i], zev[2 * i + 1])); last_z_ms += ms; }
@@ -872,6 +880,8 @@ struct Sampler : bnmf_handle {
     if (!strcmp(name, "A")) { if (len != cfg.N) return fail("bnmf_get_sample: A has %d elements", cfg.N); return dev_to_host(d.ring_A + (long long)slot * cfg.N, ST_I32, cfg.N, out); }
     return fail("bnmf_get_sample: the ring holds P, E and A (got '%s')", name);
   }
+  int run(const bnmf_convergence_control* cc, int post_warmup, double* metrics_out, int64_t rows_cap,
+          double* map_out, int64_t checks_cap, bnmf_run_result* res) override;
   int get_map(int n_samples, double* P, double* E, double* A, int* n_match) override;
   int get_ci(int n_samples, double plo, double phi, double* P_lo, double* P_hi, double* E_lo, double* E_hi, int* n_match) override;
   int map_slots(int n_samples, std::vector<int>& match, std::string& mode);
@@ -943,6 +953,7 @@ template <typename T> int Sampler<T>::refresh_colsumP() {
 
 #include "bnmf_api_mh.inl"
 #include "bnmf_api_map.inl"
+#include "bnmf_api_run.inl"
 
 // ---------------------------------------------------------------------------------
 // extern "C"
@@ -998,6 +1009,9 @@ int bnmf_get_state(bnmf_handle* h, const char* name, double* out, int64_t len) {
 int bnmf_set_temperature_schedule(bnmf_handle* h, const double* t, int64_t n) { NEED(h); return h->set_temps(t, n); }
 int bnmf_init_from_prior(bnmf_handle* h, uint32_t have, uint32_t have_prior, double* row) { NEED(h); return h->init_from_prior(have, have_prior, row); }
 int bnmf_step(bnmf_handle* h, int32_t n, int32_t conv, double* m, double* P, double* A) { NEED(h); return h->step(n, conv, m, P, A); }
+int bnmf_run(bnmf_handle* h, const bnmf_convergence_control* cc, int32_t pw, double* m, int64_t rc, double* mm, int64_t cc_cap, bnmf_run_result* res) {
+  NEED(h); return h->run(cc, pw, m, rc, mm, cc_cap, res);
+}
 int bnmf_ring_count(bnmf_handle* h, int32_t* c) { NEED(h); return h->ring_count(c); }
 int bnmf_get_sample(bnmf_handle* h, const char* name, int32_t ago, double* out, int64_t len) { NEED(h); return h->get_sample(name, ago, out, len); }
 int bnmf_get_map(bnmf_handle* h, int32_t n, double* P, double* E, double* A, int32_t* nm) { NEED(h); return h->get_map(n, P, E, A, nm); }

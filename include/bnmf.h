@@ -131,6 +131,39 @@ int bnmf_get_credible_intervals(bnmf_handle* h, int32_t n_samples, double lower_
                                 double* P_lower, double* P_upper, double* E_lower, double* E_upper,
                                 int32_t* n_match);
 
+/* run_gibbs_sampler (R/bayesNMF_sampler.R:265-408) with the convergence control of
+ * R/convergence.R:60-154 and update_MAP_metrics_ (R/utils.R:356-397) behind the ABI: blocks of
+ * iterations up to the next MAP check, the window mean of the metric, percent change, the
+ * "no change" / "no best" / "max iters" rules (only once every temperature of the window is 1 and
+ * iter >= miniters), then -- Metropolis-Hastings models -- `post_warmup` iterations with the real
+ * accept step.  One call replaces a host round trip every MAP_every iterations.
+ * The metric is a window mean of sample_metrics (logposterior, loglikelihood) or the BIC built
+ * from it; RMSE / KL of the MAP reconstruction are not offered here (use bnmf_step + bnmf_get_map). */
+enum { BNMF_METRIC_LOGPOSTERIOR = 0, BNMF_METRIC_LOGLIKELIHOOD = 1, BNMF_METRIC_BIC = 2 };
+enum { BNMF_WHY_NONE = 0, BNMF_WHY_NO_CHANGE = 1, BNMF_WHY_NO_BEST = 2, BNMF_WHY_MAX_ITERS = 3 };
+typedef struct bnmf_convergence_control {   /* new_convergence_control, R/convergence.R:16-45 */
+  int32_t MAP_over, MAP_every;
+  double tol;
+  int32_t Ninarow_nochange, Ninarow_nobest, miniters, maxiters;
+  int32_t metric;                           /* BNMF_METRIC_* */
+} bnmf_convergence_control;
+/* one row of state$MAP_metrics per check */
+enum { BNMF_MM_ITER = 0, BNMF_MM_LOGLIK, BNMF_MM_LOGPOST, BNMF_MM_NPARAMS, BNMF_MM_BIC, BNMF_MM_RANK,
+       BNMF_MM_A_COUNTS, BNMF_MM_MEAN_TEMP, BNMF_MM_COLS };
+typedef struct bnmf_run_result {
+  int32_t iter;             /* state$iter at return */
+  int32_t converged, converged_iter, why;   /* BNMF_WHY_* */
+  int32_t best_iter, n_checks, n_rows;
+  int32_t inarow_no_change, inarow_no_best, inarow_na;
+  double best_MAP_metric, prev_MAP_metric;
+} bnmf_run_result;
+/*   metrics_out      NULL or rows_cap x BNMF_MC_COLS: the sample_metrics rows of the iterations run
+ *   map_metrics_out  NULL or checks_cap x BNMF_MM_COLS: the MAP_metrics rows of the checks made
+ * The handle needs ring_cap >= MAP_over (the MAP of a check comes from the device ring). */
+int bnmf_run(bnmf_handle* h, const bnmf_convergence_control* cc, int32_t post_warmup,
+             double* metrics_out, int64_t rows_cap, double* map_metrics_out, int64_t checks_cap,
+             bnmf_run_result* result);
+
 /* Cross-shard reduction for genome-sharded runs (one process per GPU): each rank
  * creates its shard handle, rank 0 makes an id, every rank joins.  Afterwards
  * bnmf_step sums SP, rowSums(E) and the metric partials over ranks with NCCL. */

@@ -85,6 +85,26 @@ b200_block <- function(self, private, converged = FALSE) {
   invisible(n)
 }
 
+# the whole of run_gibbs_sampler() in one call (convergence control behind the ABI); fills
+# state$sample_metrics, state$MAP_metrics (loglikelihood, logposterior, n_params, BIC, rank, A counts,
+# mean temperature per check), state$iter / converged / converged_iter / why, then the MAP
+b200_run <- function(self, private) {
+  cc <- self$specs$convergence_control
+  metric_id <- c(logposterior = 0, loglikelihood = 1, BIC = 2)[[cc$metric]]
+  out <- .Call("R_bnmf_run", private$h,
+               as.numeric(c(cc$MAP_over, cc$MAP_every, cc$tol, cc$Ninarow_nochange, cc$Ninarow_nobest, cc$miniters, cc$maxiters, metric_id)),
+               as.integer(if (self$specs$MH) self$specs$post_warmup else 0L))
+  r <- out[[1]]
+  b200_append_metrics(self, t(out[[2]][, seq_len(r[6]), drop = FALSE]))
+  mm <- as.data.frame(t(out[[3]][, seq_len(r[7]), drop = FALSE]))
+  names(mm) <- c("iter", "loglikelihood", "logposterior", "n_params", "BIC", "rank", "MAP_A_counts", "mean_temp")
+  self$state$MAP_metrics <- mm
+  self$state$iter <- r[1]; self$state$converged <- r[2] == 1; self$state$converged_iter <- r[3]
+  self$state$why <- c("no change", "no best", "max iters")[r[4]]
+  b200_pull_state(self, private)
+  invisible(self)
+}
+
 # get_MAP_ (R/utils.R:194-288) on the device ring: mode of A, renormalise, mean over the matching
 # samples; samples$E never crosses PCIe unless credible intervals over E are wanted on the host
 b200_get_MAP <- function(self, private, n_samples) {

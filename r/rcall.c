@@ -112,6 +112,29 @@ SEXP R_bnmf_step(SEXP p, SEXP n, SEXP converged, SEXP K, SEXP N) {
   CK(rc);
   return out;
 }
+/* run_gibbs_sampler with the convergence control behind the ABI (R/bayesNMF_sampler.R:265-408,
+ * R/convergence.R:60-154): cc = c(MAP_over, MAP_every, tol, Ninarow_nochange, Ninarow_nobest, miniters,
+ * maxiters, metric id); list(result = c(iter, converged, converged_iter, why, best_iter), metrics, MAP_metrics) */
+SEXP R_bnmf_run(SEXP p, SEXP cc, SEXP post_warmup) {
+  bnmf_convergence_control c;
+  const double* v = REAL(cc);
+  c.MAP_over = (int32_t)v[0]; c.MAP_every = (int32_t)v[1]; c.tol = v[2]; c.Ninarow_nochange = (int32_t)v[3];
+  c.Ninarow_nobest = (int32_t)v[4]; c.miniters = (int32_t)v[5]; c.maxiters = (int32_t)v[6]; c.metric = (int32_t)v[7];
+  const int pw = Rf_asInteger(post_warmup);
+  const int rows = c.maxiters + pw + 8, checks = rows / (c.MAP_every > 0 ? c.MAP_every : 1) + 8;
+  SEXP met = PROTECT(Rf_allocMatrix(REALSXP, BNMF_MC_COLS, rows));
+  SEXP mm = PROTECT(Rf_allocMatrix(REALSXP, BNMF_MM_COLS, checks));
+  bnmf_run_result r;
+  int rc = bnmf_run(H(p), &c, pw, REAL(met), rows, REAL(mm), checks, &r);
+  SEXP res = PROTECT(Rf_allocVector(REALSXP, 7));
+  REAL(res)[0] = r.iter; REAL(res)[1] = r.converged; REAL(res)[2] = r.converged_iter; REAL(res)[3] = r.why;
+  REAL(res)[4] = r.best_iter; REAL(res)[5] = r.n_rows; REAL(res)[6] = r.n_checks;
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, res); SET_VECTOR_ELT(out, 1, met); SET_VECTOR_ELT(out, 2, mm);
+  UNPROTECT(4);
+  CK(rc);
+  return out;
+}
 /* get_MAP_, R/utils.R:194-288, on the device ring: list(P, E, A, n_match) */
 SEXP R_bnmf_get_map(SEXP p, SEXP n_samples, SEXP K, SEXP N, SEXP G) {
   int k = Rf_asInteger(K), nn = Rf_asInteger(N), g = Rf_asInteger(G);
@@ -187,7 +210,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bnmf_set_state", (DL_FUNC)&R_bnmf_set_state, 3},     {"R_bnmf_get_state", (DL_FUNC)&R_bnmf_get_state, 4},
   {"R_bnmf_set_temps", (DL_FUNC)&R_bnmf_set_temps, 2},     {"R_bnmf_init", (DL_FUNC)&R_bnmf_init, 3},
   {"R_bnmf_step", (DL_FUNC)&R_bnmf_step, 5},               {"R_bnmf_get_map", (DL_FUNC)&R_bnmf_get_map, 5},
-  {"R_bnmf_get_ci", (DL_FUNC)&R_bnmf_get_ci, 6},
+  {"R_bnmf_get_ci", (DL_FUNC)&R_bnmf_get_ci, 6},           {"R_bnmf_run", (DL_FUNC)&R_bnmf_run, 3},
   {"R_bnmf_get_sample", (DL_FUNC)&R_bnmf_get_sample, 5},   {"R_bnmf_ring_count", (DL_FUNC)&R_bnmf_ring_count, 1},
   {"R_bnmf_comm_unique_id", (DL_FUNC)&R_bnmf_comm_unique_id, 0}, {"R_bnmf_comm_init", (DL_FUNC)&R_bnmf_comm_init, 4},
   {"R_bnmf_comm_share", (DL_FUNC)&R_bnmf_comm_share, 2},   {"R_bnmf_timing", (DL_FUNC)&R_bnmf_timing, 1},

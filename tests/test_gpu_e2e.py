@@ -69,3 +69,31 @@ def test_bic_fan_out(built_lib):
     assert [r["BIC"] for r in out["results"]] == sorted(r["BIC"] for r in out["results"])
     assert out["best_rank"] in (3, 4) and out["sampler"].dims["N"] == out["best_rank"]
     out["sampler"].close()
+
+
+@pytest.mark.parametrize("model", ["default", "fixed"])
+def test_run_behind_the_abi_equals_host_loop(built_lib, model):
+    """bnmf_run (run_gibbs_sampler + check_convergence_ + the MAP-metric windows behind the ABI,
+    SURVEY.md section 8 f-4) makes the same decisions as the host mirror of the R loop: same stop
+    iteration and reason, same sample_metrics rows, same MAP_metrics at every check."""
+    from bayesnmf_b200 import bayesNMF_sampler, new_convergence_control
+    M, _ = example_data()
+    cc = new_convergence_control(MAP_over=300, MAP_every=100, miniters=600, maxiters=1500)
+    if model == "default":
+        kw = dict(rank=np.arange(1, 9), post_warmup=300)                          # Poisson-TruncNormal + MH, SBFI
+    else:
+        kw = dict(rank=4, likelihood="poisson", prior="gamma")                     # fixed rank, latent counts
+    a = bayesNMF_sampler(M, convergence_control=cc, seed=5, **kw).run_gibbs_sampler()
+    b = bayesNMF_sampler(M, convergence_control=cc, seed=5, **kw)
+    r = b._h.run(cc, post_warmup=b.specs.get("post_warmup", 0))
+    assert r["converged"] == int(a.state["converged"]) and r["why"] == a.state.get("why")
+    assert r["converged_iter"] == a.state.get("converged_iter", 0) and r["iter"] == a.state["iter"]
+    sm = a.state["sample_metrics"]
+    np.testing.assert_array_equal(r["metrics"][:, 0], np.asarray(sm["iter"])[1:])
+    np.testing.assert_allclose(r["metrics"][:, 4], np.asarray(sm["logposterior"])[1:], rtol=0, atol=0)
+    assert len(r["MAP_metrics"]) == len(a.state["MAP_metrics"])
+    for x, y in zip(r["MAP_metrics"], a.state["MAP_metrics"]):
+        for key in ("iter", "loglikelihood", "logposterior", "n_params", "BIC", "rank", "MAP_A_counts", "mean_temp"):
+            np.testing.assert_allclose(x[key], y[key], rtol=1e-12, err_msg=key)
+    assert r["best_iter"] == a.state.get("best_iter", 0)
+    a.close(); b.close()
