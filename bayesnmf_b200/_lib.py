@@ -64,6 +64,8 @@ def lib():
     L.bnmf_init_from_prior.argtypes = [vp, u32, u32, dp]
     L.bnmf_step.argtypes = [vp, i32, i32, dp, dp, dp]
     L.bnmf_run.argtypes = [vp, ctypes.c_void_p, i32, dp, i64, dp, i64, ctypes.c_void_p]
+    ip = ctypes.POINTER(i32)
+    L.bnmf_assign_signatures.argtypes = [vp, i32, dp, i32, ctypes.c_double, ip, ip, dp, ip, dp, dp, dp, ip]
     L.bnmf_ring_count.argtypes = [vp, ctypes.POINTER(i32)]
     L.bnmf_get_sample.argtypes = [vp, cp, i32, dp, i64]
     L.bnmf_get_map.argtypes = [vp, i32, dp, dp, dp, ctypes.POINTER(i32)]
@@ -99,7 +101,7 @@ MAP_METRIC_NAMES = ["iter", "loglikelihood", "logposterior", "n_params", "BIC", 
 
 EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
            "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
-           "bnmf_step", "bnmf_run", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_get_credible_intervals", "bnmf_comm_unique_id",
+           "bnmf_step", "bnmf_run", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_get_credible_intervals", "bnmf_assign_signatures", "bnmf_comm_unique_id",
            "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z"]
 
 
@@ -232,6 +234,24 @@ class Handle:
         out["metrics"] = met[:res.n_rows]
         out["MAP_metrics"] = [dict(zip(MAP_METRIC_NAMES, r)) for r in mm[:res.n_checks]]
         return out
+
+    def assign_signatures(self, n_samples, reference_P, credible_interval=0.95):
+        """assign_signatures_ensemble_ (R/postprocessing.R:175-341) over the retained samples: dict(keep_sigs,
+        assignment (reference column per included signature), votes (n_keep x n_ref shares), MAP_cosine,
+        lower_cosine, upper_cosine, n_match)."""
+        ref = np.asarray(reference_P, dtype=np.float64)
+        if ref.shape[0] != self.K:
+            raise ValueError(f"Reference matrix has {ref.shape[0]} rows, but data has {self.K} rows.")
+        R = ref.shape[1]
+        i32a = lambda n: np.zeros(n, dtype=np.int32)
+        nk, nm, keep, asg = ctypes.c_int32(), ctypes.c_int32(), i32a(self.N), i32a(self.N)
+        votes = np.zeros(self.N * R); mc, lo, hi = np.zeros(self.N), np.zeros(self.N), np.zeros(self.N)
+        ipt = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        self._ck(lib().bnmf_assign_signatures(self._h, int(n_samples), _dp(_f64(ref)), R, float(credible_interval), ctypes.byref(nk),
+                                              ipt(keep), _dp(votes), ipt(asg), _dp(mc), _dp(lo), _dp(hi), ctypes.byref(nm)))
+        k = nk.value
+        return dict(keep_sigs=keep[:k].copy(), assignment=asg[:k].copy(), votes=votes.reshape((self.N, R), order="F")[:k].copy(),
+                    MAP_cosine=mc[:k].copy(), lower_cosine=lo[:k].copy(), upper_cosine=hi[:k].copy(), n_match=nm.value)
 
     def get_credible_intervals(self, n_samples, lower_p=0.025, upper_p=0.975):
         """(P_lower, P_upper, E_lower, E_upper, n_match): element-wise quantiles over the samples that

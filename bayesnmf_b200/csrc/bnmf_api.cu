@@ -86,6 +86,8 @@ struct bnmf_handle {
   virtual int ring_count(int* c) = 0;
   virtual int get_sample(const char* name, int ago, double* out, int64_t len) = 0;
   virtual int get_map(int n_samples, double* P, double* E, double* A, int* n_match) = 0;
+  virtual int assign(int n_samples, const double* ref, int n_ref, double ci, int* n_keep, int* keep, double* votes, int* asg,
+                     double* mapc, double* lo, double* hi, int* n_match) = 0;
   virtual int get_ci(int n_samples, double plo, double phi, double* P_lo, double* P_hi, double* E_lo, double* E_hi, int* n_match) = 0;
   virtual int comm_init(const char* id, int rank, int world) = 0;
   virtual int comm_share(bnmf_handle* src) = 0;
@@ -885,6 +887,8 @@ struct Sampler : bnmf_handle {
   int get_map(int n_samples, double* P, double* E, double* A, int* n_match) override;
   int get_ci(int n_samples, double plo, double phi, double* P_lo, double* P_hi, double* E_lo, double* E_hi, int* n_match) override;
   int map_slots(int n_samples, std::vector<int>& match, std::string& mode);
+  int assign(int n_samples, const double* ref, int n_ref, double ci, int* n_keep, int* keep, double* votes, int* asg,
+             double* mapc, double* lo, double* hi, int* n_match) override;
 
   int set_l2_flush(size_t bytes) override {
     CK(cudaSetDevice(cfg.device));
@@ -1015,6 +1019,10 @@ int bnmf_run(bnmf_handle* h, const bnmf_convergence_control* cc, int32_t pw, dou
 int bnmf_ring_count(bnmf_handle* h, int32_t* c) { NEED(h); return h->ring_count(c); }
 int bnmf_get_sample(bnmf_handle* h, const char* name, int32_t ago, double* out, int64_t len) { NEED(h); return h->get_sample(name, ago, out, len); }
 int bnmf_get_map(bnmf_handle* h, int32_t n, double* P, double* E, double* A, int32_t* nm) { NEED(h); return h->get_map(n, P, E, A, nm); }
+int bnmf_assign_signatures(bnmf_handle* h, int32_t n, const double* ref, int32_t n_ref, double ci, int32_t* n_keep, int32_t* keep, double* votes,
+                           int32_t* asg, double* mapc, double* lo, double* hi, int32_t* nm) {
+  NEED(h); return h->assign(n, ref, n_ref, ci, n_keep, keep, votes, asg, mapc, lo, hi, nm);
+}
 int bnmf_get_credible_intervals(bnmf_handle* h, int32_t n, double plo, double phi, double* P_lo, double* P_hi, double* E_lo, double* E_hi, int32_t* nm) {
   NEED(h); return h->get_ci(n, plo, phi, P_lo, P_hi, E_lo, E_hi, nm);
 }

@@ -180,3 +180,132 @@ template <typename T> int Sampler<T>::get_ci(int n_samples, double plo, double p
   if (n_match_out) *n_match_out = nm;
   return 0;
 }
+
+// ---- assign_signatures_ensemble_ (R/postprocessing.R:175-341) ---------------------------------------
+// cos[s][i][j] = cosine(P_s[, keep[i]], ref[, j]) for the matching ring slots (s = n_match: the MAP
+// signatures, mean of the renormalised samples); a block per (i, s), threads over j
+template <typename T> static __global__ void k_assign_cos(Dev<T> d, const int* slots, int nm, const int* keep, int n_keep,
+                                                           const double* ref, int n_ref, const double* Pmap, double* cosv) {
+  extern __shared__ double col[];                 // [K] the estimated signature
+  __shared__ double scratch[4];
+  const int i = blockIdx.x, s = blockIdx.y, K = d.K;
+  const int n = keep[i];
+  double ss = 0.0;
+  for (int k = threadIdx.x; k < K; k += 128) {
+    const double v = s < nm ? (double)d.ring_P[(long long)slots[s] * K * d.N + (long long)K * n + k] : Pmap[(long long)K * n + k];
+    col[k] = v; ss += v * v;
+  }
+  __shared__ double norm_e;
+  const double tot = block_sum<128>(ss, scratch);
+  if (threadIdx.x == 0) norm_e = sqrt(tot);
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_ref; j += 128) {
+    double dot = 0.0, rr = 0.0;
+    for (int k = 0; k < K; ++k) { const double r = ref[(long long)K * j + k]; dot += col[k] * r; rr += r * r; }
+    cosv[((long long)s * n_keep + i) * n_ref + j] = dot / (norm_e * sqrt(rr));     // lsa::cosine
+  }
+}
+
+// minimum-cost assignment of n rows to m >= n columns (Hungarian algorithm with potentials, O(n^2 m));
+// cost row-major n x m; asg[i] = column of row i
+static void hungarian(const std::vector<double>& cost, int n, int m, std::vector<int>& asg) {
+  const double INF = 1e300;
+  std::vector<double> u(n + 1, 0.0), v(m + 1, 0.0);
+  std::vector<int> p(m + 1, 0), way(m + 1, 0);
+  for (int i = 1; i <= n; ++i) {
+    p[0] = i;
+    int j0 = 0;
+    std::vector<double> minv(m + 1, INF);
+    std::vector<char> used(m + 1, 0);
+    do {
+      used[j0] = 1;
+      const int i0 = p[j0];
+      double delta = INF; int j1 = 0;
+      for (int j = 1; j <= m; ++j) if (!used[j]) {
+        const double cur = cost[(size_t)(i0 - 1) * m + (j - 1)] - u[i0] - v[j];
+        if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
+        if (minv[j] < delta) { delta = minv[j]; j1 = j; }
+      }
+      for (int j = 0; j <= m; ++j) {
+        if (used[j]) { u[p[j]] += delta; v[j] -= delta; } else minv[j] -= delta;
+      }
+      j0 = j1;
+    } while (p[j0] != 0);
+    do { const int j1 = way[j0]; p[j0] = p[j1]; j0 = j1; } while (j0);
+  }
+  asg.assign(n, -1);
+  for (int j = 1; j <= m; ++j) if (p[j]) asg[p[j] - 1] = j - 1;
+}
+
+template <typename T> int Sampler<T>::assign(int n_samples, const double* ref, int n_ref, double ci, int* n_keep_out, int* keep_out,
+                                             double* votes, int* asg_out, double* mapc, double* lo_out, double* hi_out, int* n_match_out) {
+  CK(cudaSetDevice(cfg.device));
+  if (!ref || n_ref < 1) return fail("bnmf_assign_signatures: a reference matrix (K x n_ref) is needed");
+  if (!(ci > 0.0 && ci < 1.0)) return fail("bnmf_assign_signatures: credible_interval must be in (0, 1)");
+  std::vector<int> match; std::string mode;
+  if (map_slots(n_samples, match, mode)) return 1;
+  const int N = cfg.N, K = cfg.K, nm = (int)match.size();
+  std::vector<int> keep;
+  for (int n = 0; n < N; ++n) if (mode[n] == '1') keep.push_back(n);
+  const int nk = (int)keep.size();
+  if (n_keep_out) *n_keep_out = nk;
+  if (n_match_out) *n_match_out = nm;
+  if (keep_out) for (int i = 0; i < nk; ++i) keep_out[i] = keep[i];
+  if (nk == 0) return 0;
+  if (nk > n_ref) return fail("bnmf_assign_signatures: %d included signatures but only %d reference signatures", nk, n_ref);
+  // MAP signatures (mean of the renormalised matching samples), then all cosines on the device
+  const long long KN = (long long)K * N;
+  int* dslots; int* dkeep; double* colsum; double* dPmap; double* dref; double* dcos;
+  CK(cudaMalloc((void**)&dslots, sizeof(int) * nm)); CK(cudaMalloc((void**)&dkeep, sizeof(int) * nk));
+  CK(cudaMalloc((void**)&colsum, sizeof(double) * (size_t)nm * N)); CK(cudaMalloc((void**)&dPmap, sizeof(double) * KN));
+  CK(cudaMalloc((void**)&dref, sizeof(double) * (size_t)K * n_ref));
+  CK(cudaMalloc((void**)&dcos, sizeof(double) * (size_t)(nm + 1) * nk * n_ref));
+  CK(cudaMemcpyAsync(dslots, match.data(), sizeof(int) * nm, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(dkeep, keep.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(dref, ref, sizeof(double) * (size_t)K * n_ref, cudaMemcpyHostToDevice, stream));
+  k_map_colsum<T><<<dim3(N, nm), 128, 0, stream>>>(d, dslots, colsum);
+  k_map_mean_P<T><<<blocks(KN, 128), 128, 0, stream>>>(d, dslots, nm, colsum, dPmap);
+  k_assign_cos<T><<<dim3(nk, nm + 1), 128, sizeof(double) * K, stream>>>(d, dslots, nm, dkeep, nk, dref, n_ref, dPmap, dcos);
+  std::vector<double> cosv((size_t)(nm + 1) * nk * n_ref);
+  CK(cudaMemcpyAsync(cosv.data(), dcos, sizeof(double) * cosv.size(), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  cudaFree(dslots); cudaFree(dkeep); cudaFree(colsum); cudaFree(dPmap); cudaFree(dref); cudaFree(dcos);
+  // votes: every sample's Hungarian assignment votes with its cosine (R/postprocessing.R:277-301)
+  std::vector<double> V((size_t)nk * n_ref, 0.0), cost((size_t)nk * n_ref);
+  std::vector<int> a;
+  for (int s = 0; s < nm; ++s) {
+    const double* cs = cosv.data() + (size_t)s * nk * n_ref;
+    for (size_t t = 0; t < cost.size(); ++t) cost[t] = -cs[t];
+    hungarian(cost, nk, n_ref, a);
+    for (int i = 0; i < nk; ++i) V[(size_t)i * n_ref + a[i]] += cs[(size_t)i * n_ref + a[i]];
+  }
+  std::vector<int> win(nk, 0);
+  for (int i = 0; i < nk; ++i) {
+    double tot = 0.0;
+    for (int j = 0; j < n_ref; ++j) tot += V[(size_t)i * n_ref + j];
+    int best = 0; double bp = -1.0;
+    for (int j = 0; j < n_ref; ++j) {
+      const double pv = V[(size_t)i * n_ref + j] / tot;
+      if (votes) votes[(size_t)i + (size_t)N * j] = pv;
+      if (pv > bp) { bp = pv; best = j; }          // which.max: the first maximum
+    }
+    win[i] = best;
+    if (asg_out) asg_out[i] = best;
+    if (mapc) mapc[i] = cosv[((size_t)nm * nk + i) * n_ref + best];
+    // credible interval of the samples' cosines to the winner, quantile type 7
+    std::vector<double> x(nm);
+    for (int s = 0; s < nm; ++s) x[s] = cosv[((size_t)s * nk + i) * n_ref + best];
+    std::sort(x.begin(), x.end());
+    const double probs[2] = {(1.0 - ci) / 2.0, 1.0 - (1.0 - ci) / 2.0};
+    for (int q = 0; q < 2; ++q) {
+      const double hh = (double)(nm - 1) * probs[q];
+      int j = (int)std::floor(hh); if (j > nm - 1) j = nm - 1;
+      const double g = hh - (double)j;
+      const double val = x[j] + g * (x[j + 1 < nm ? j + 1 : nm - 1] - x[j]);
+      if (q == 0 && lo_out) lo_out[i] = val;
+      if (q == 1 && hi_out) hi_out[i] = val;
+    }
+  }
+  return 0;
+}

@@ -131,6 +131,24 @@ int bnmf_get_credible_intervals(bnmf_handle* h, int32_t n_samples, double lower_
                                 double* P_lower, double* P_upper, double* E_lower, double* E_upper,
                                 int32_t* n_match);
 
+/* assign_signatures_ensemble_ (R/postprocessing.R:175-341) on the retained samples: over the
+ * newest `n_samples` ring samples that match the modal A, and over the included signatures
+ * (keep_sigs: A == 1), every sample's P is assigned to the reference signatures by the Hungarian
+ * algorithm on minus the cosine similarity (hungarian_assignment, R/helpers.R:287-362; the cosines
+ * are computed on the device), an assignment votes with its cosine, the reference with the largest
+ * share of an estimated signature's votes wins; MAP_cosine is the cosine of the MAP signature to its
+ * winner, lower / upper the type-7 quantiles (1 +- credible_interval) / 2 of the samples' cosines to it.
+ *   reference_P  K x n_ref, column-major (e.g. the 79 COSMIC SBS signatures)
+ *   keep_sigs    N      0-based indices of the included signatures (first *n_keep entries valid)
+ *   votes        N x n_ref, column-major with leading dimension N: votes[i + N*j] = share of the votes of
+ *                estimated signature keep_sigs[i] that went to reference j (rows i < *n_keep)
+ *   assignment   N      0-based reference index per included signature
+ *   map_cosine, lower_cosine, upper_cosine   N each (first *n_keep entries valid) */
+int bnmf_assign_signatures(bnmf_handle* h, int32_t n_samples, const double* reference_P, int32_t n_ref,
+                           double credible_interval, int32_t* n_keep, int32_t* keep_sigs, double* votes,
+                           int32_t* assignment, double* map_cosine, double* lower_cosine, double* upper_cosine,
+                           int32_t* n_match);
+
 /* run_gibbs_sampler (R/bayesNMF_sampler.R:265-408) with the convergence control of
  * R/convergence.R:60-154 and update_MAP_metrics_ (R/utils.R:356-397) behind the ABI: blocks of
  * iterations up to the next MAP check, the window mean of the metric, percent change, the

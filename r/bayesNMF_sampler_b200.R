@@ -117,5 +117,19 @@ b200_credible_intervals <- function(self, private, n_samples, credible_interval 
   r <- .Call("R_bnmf_get_ci", private$h, as.integer(n_samples), probs, self$dims$K, self$dims$N, self$dims$G)
   list(P = list(lower = r[[1]], upper = r[[2]]), E = list(lower = r[[3]], upper = r[[4]]))
 }
+# assign_signatures_ensemble_ (R/postprocessing.R:175-341) over the retained samples; returns the
+# `assignments` and `votes` data frames the reference stores in self$reference_comparison
+b200_assign_signatures <- function(self, private, reference_P, n_samples, credible_interval = 0.95) {
+  r <- .Call("R_bnmf_assign_signatures", private$h, as.integer(n_samples), reference_P, credible_interval, self$dims$N)
+  nk <- r[[7]]; i <- seq_len(nk)
+  ref_names <- if (is.null(colnames(reference_P))) paste0("Ref", seq_len(ncol(reference_P))) else colnames(reference_P)
+  assignments <- data.frame(sig_est = r[[1]][i], sig_ref = ref_names[r[[2]][i]], MAP_cosine = r[[4]][i],
+                            lower_cosine = r[[5]][i], upper_cosine = r[[6]][i])
+  v <- r[[3]][i, , drop = FALSE]
+  w <- which(v > 0, arr.ind = TRUE)
+  votes <- data.frame(sig_est = r[[1]][w[, 1]], sig_ref = ref_names[w[, 2]], prop_votes = v[w])
+  votes <- votes[order(votes$sig_est, -votes$prop_votes), ]
+  list(assignments = assignments, votes = votes)
+}
 b200_sample_E <- function(self, private, ago = 0L)
   .Call("R_bnmf_get_sample", private$h, "E", as.integer(ago), self$dims$N, self$dims$G)

@@ -166,6 +166,27 @@ SEXP R_bnmf_get_ci(SEXP p, SEXP n_samples, SEXP probs, SEXP K, SEXP N, SEXP G) {
   CK(rc);
   return out;
 }
+/* assign_signatures_ensemble_, R/postprocessing.R:175-341, over the retained samples:
+ * list(keep_sigs (1-based), sig_ref (1-based column of reference_P), votes (n_keep x n_ref shares),
+ *      MAP_cosine, lower_cosine, upper_cosine, n_match) */
+SEXP R_bnmf_assign_signatures(SEXP p, SEXP n_samples, SEXP reference_P, SEXP credible_interval, SEXP N) {
+  const int nn = Rf_asInteger(N), n_ref = Rf_ncols(reference_P);
+  SEXP ref = PROTECT(Rf_coerceVector(reference_P, REALSXP));
+  SEXP votes = PROTECT(Rf_allocMatrix(REALSXP, nn, n_ref));
+  SEXP mc = PROTECT(Rf_allocVector(REALSXP, nn)), lo = PROTECT(Rf_allocVector(REALSXP, nn)), hi = PROTECT(Rf_allocVector(REALSXP, nn));
+  SEXP keep = PROTECT(Rf_allocVector(REALSXP, nn)), sig = PROTECT(Rf_allocVector(REALSXP, nn));
+  int32_t nk = 0, nm = 0, keep_i[64], asg_i[64];
+  memset(REAL(votes), 0, sizeof(double) * (size_t)nn * n_ref);
+  int rc = nn > 64 ? 1 : bnmf_assign_signatures(H(p), Rf_asInteger(n_samples), REAL(ref), n_ref, Rf_asReal(credible_interval), &nk,
+                                                keep_i, REAL(votes), asg_i, REAL(mc), REAL(lo), REAL(hi), &nm);
+  for (int i = 0; i < nn; ++i) { REAL(keep)[i] = i < nk ? keep_i[i] + 1 : 0; REAL(sig)[i] = i < nk ? asg_i[i] + 1 : 0; }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 8));
+  SET_VECTOR_ELT(out, 0, keep); SET_VECTOR_ELT(out, 1, sig); SET_VECTOR_ELT(out, 2, votes); SET_VECTOR_ELT(out, 3, mc);
+  SET_VECTOR_ELT(out, 4, lo); SET_VECTOR_ELT(out, 5, hi); SET_VECTOR_ELT(out, 6, Rf_ScalarInteger(nk)); SET_VECTOR_ELT(out, 7, Rf_ScalarInteger(nm));
+  UNPROTECT(8);
+  CK(rc);
+  return out;
+}
 /* samples$E[[i]] on demand (update_list ring, R/helpers.R:111-119); ago = 0 is the newest */
 SEXP R_bnmf_get_sample(SEXP p, SEXP name, SEXP ago, SEXP nrow, SEXP ncol) {
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(nrow), Rf_asInteger(ncol)));
@@ -211,6 +232,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bnmf_set_temps", (DL_FUNC)&R_bnmf_set_temps, 2},     {"R_bnmf_init", (DL_FUNC)&R_bnmf_init, 3},
   {"R_bnmf_step", (DL_FUNC)&R_bnmf_step, 5},               {"R_bnmf_get_map", (DL_FUNC)&R_bnmf_get_map, 5},
   {"R_bnmf_get_ci", (DL_FUNC)&R_bnmf_get_ci, 6},           {"R_bnmf_run", (DL_FUNC)&R_bnmf_run, 3},
+  {"R_bnmf_assign_signatures", (DL_FUNC)&R_bnmf_assign_signatures, 5},
   {"R_bnmf_get_sample", (DL_FUNC)&R_bnmf_get_sample, 5},   {"R_bnmf_ring_count", (DL_FUNC)&R_bnmf_ring_count, 1},
   {"R_bnmf_comm_unique_id", (DL_FUNC)&R_bnmf_comm_unique_id, 0}, {"R_bnmf_comm_init", (DL_FUNC)&R_bnmf_comm_init, 4},
   {"R_bnmf_comm_share", (DL_FUNC)&R_bnmf_comm_share, 2},   {"R_bnmf_timing", (DL_FUNC)&R_bnmf_timing, 1},

@@ -61,3 +61,47 @@ def test_map_without_ring_fails(built_lib):
     h.init_from_prior()
     with pytest.raises(BnmfError):
         h.get_map(1)
+
+
+def test_assign_signatures_ensemble(built_lib):
+    """assign_signatures_ensemble_ (R/postprocessing.R:175-341) on the retained samples against a host
+    restatement with scipy's Hungarian solver: votes, winners, MAP cosine, credible interval of the
+    samples' cosines; and the tutorial's known answer -- the planted COSMIC signatures win."""
+    from scipy.optimize import linear_sum_assignment
+    from bayesnmf_b200 import Handle
+    from oracle.gibbs import get_MAP
+    from tests.util import cosmic, example_data
+    M, Ptrue = example_data()
+    C, names, _ = cosmic()
+    N, cap = 4, 40
+    h = Handle(M, N, likelihood="poisson", prior="gamma", MH=False, seed=3, ring_cap=cap)
+    h.init_from_prior()
+    h.step(400)
+    Ps = [h.get_sample("P", cap - 1 - i) for i in range(cap)]           # oldest first
+    Es = [h.get_sample("E", cap - 1 - i) for i in range(cap)]
+    As = [h.get_sample("A", cap - 1 - i) for i in range(cap)]
+    r = h.assign_signatures(cap, C, credible_interval=0.9)
+    P_map, _, A_map, idx = get_MAP(Ps, Es, As)
+    keep = np.nonzero(A_map == 1)[0]
+    assert r["n_match"] == len(idx) and np.array_equal(r["keep_sigs"], keep)
+    cosf = lambda A, B: (A.T @ B) / np.outer(np.linalg.norm(A, axis=0), np.linalg.norm(B, axis=0))
+    V = np.zeros((len(keep), C.shape[1]))
+    sims = []
+    for i in idx:
+        S = cosf(Ps[i][:, keep], C)
+        rows, cols = linear_sum_assignment(-S)
+        V[rows, cols] += S[rows, cols]
+        sims.append(S)
+    prop = V / V.sum(axis=1, keepdims=True)
+    np.testing.assert_allclose(r["votes"], prop, rtol=1e-10, atol=1e-15)
+    win = prop.argmax(axis=1)
+    assert np.array_equal(r["assignment"], win)
+    np.testing.assert_allclose(r["MAP_cosine"], cosf(P_map[:, keep], C)[np.arange(len(keep)), win], rtol=1e-10)
+    sc = np.stack([S[np.arange(len(keep)), win] for S in sims])
+    np.testing.assert_allclose(r["lower_cosine"], np.quantile(sc, 0.05, axis=0), rtol=1e-10)
+    np.testing.assert_allclose(r["upper_cosine"], np.quantile(sc, 0.95, axis=0), rtol=1e-10)
+    # the planted signatures of the example (columns of Ptrue are COSMIC SBS58, SBS40, SBS26, SBS2)
+    planted = {names[int(np.argmax(cosf(Ptrue[:, [j]], C)))] for j in range(Ptrue.shape[1])}
+    assert {names[j] for j in r["assignment"]} == planted, (r["assignment"], planted)
+    assert (r["MAP_cosine"] > 0.93).all() and (r["lower_cosine"] <= r["MAP_cosine"] + 0.02).all()
+    h.close()
