@@ -177,6 +177,23 @@ class bayesNMF_sampler:
             self.credible_intervals = dict(P=dict(lower=Pl[:, keep_sigs], upper=Ph[:, keep_sigs]),
                                            E=dict(lower=El[keep_sigs, :], upper=Eh[keep_sigs, :]))
 
+    def assign_signatures_ensemble(self, reference_P, reference_names=None, credible_interval=0.95):
+        """assign_signatures_ensemble_ (R/postprocessing.R:175-341) over the samples behind the current MAP:
+        dict(assignments = rows of (sig_est, sig_ref, MAP_cosine, lower_cosine, upper_cosine),
+             votes = rows of (sig_est, sig_ref, prop_votes)), stored in self.reference_comparison."""
+        cc = self.specs["convergence_control"]
+        n_s = min(cc["MAP_over"], self._h.ring_count())
+        r = self._h.assign_signatures(n_s, reference_P, credible_interval)
+        nm = (lambda j: reference_names[j]) if reference_names is not None else (lambda j: f"Ref{j + 1}")
+        assignments = [dict(sig_est=int(k) + 1, sig_ref=nm(int(a)), MAP_cosine=float(c), lower_cosine=float(lo), upper_cosine=float(hi))
+                       for k, a, c, lo, hi in zip(r["keep_sigs"], r["assignment"], r["MAP_cosine"], r["lower_cosine"], r["upper_cosine"])]
+        votes = []
+        for i, k in enumerate(r["keep_sigs"]):
+            order = np.argsort(-r["votes"][i], kind="stable")
+            votes += [dict(sig_est=int(k) + 1, sig_ref=nm(int(j)), prop_votes=float(r["votes"][i, j])) for j in order if r["votes"][i, j] > 0]
+        self.reference_comparison = dict(reference_P=np.asarray(reference_P), assignments=assignments, votes=votes)
+        return dict(assignments=assignments, votes=votes)
+
     def _update_MAP_metrics(self, final=False):
         """update_MAP_metrics_ + compute_metrics_(MAP = TRUE) (R/utils.R:356-397, :412-455)."""
         cc = self.specs["convergence_control"]

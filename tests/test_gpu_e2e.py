@@ -44,6 +44,13 @@ def test_tutorial_example_rank_and_signatures(built_lib, seed):
     assert lo.shape == (96, 4) and np.all(lo <= s.MAP["P"] + 1e-12) and np.all(s.MAP["P"] <= up + 1e-12)
     assert s.credible_intervals["E"]["lower"].shape == (4, 64)
     assert s.state["MAP_metrics"][-1]["rank"] == 4
+    # assign_signatures_ensemble_ (tutorial p.12-13): the four planted COSMIC signatures are recovered
+    from tests.util import cosmic
+    C, names, _ = cosmic()
+    rc = s.assign_signatures_ensemble(C, names)
+    planted = {names[int(np.argmax(_cos(Ptrue[:, [j]], C)))] for j in range(4)}
+    assert {a["sig_ref"] for a in rc["assignments"]} == planted
+    assert all(a["lower_cosine"] <= a["upper_cosine"] for a in rc["assignments"])
     s.close()
 
 
