@@ -76,6 +76,7 @@ def lib():
     L.bnmf_timing.argtypes = [vp, dp, dp, dp, ctypes.POINTER(i64)]
     L.bnmf_set_l2_flush.argtypes = [vp, ctypes.c_size_t]
     L.bnmf_sample_z.argtypes = [vp, i32, dp]
+    L.bnmf_release_cached_memory.argtypes = []
     _lib = L
     return L
 
@@ -102,7 +103,8 @@ MAP_METRIC_NAMES = ["iter", "loglikelihood", "logposterior", "n_params", "BIC", 
 EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
            "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
            "bnmf_step", "bnmf_run", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_get_credible_intervals", "bnmf_assign_signatures", "bnmf_comm_unique_id",
-           "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z"]
+           "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z",
+           "bnmf_release_cached_memory"]
 
 
 def _dp(a):
@@ -288,6 +290,12 @@ class Handle:
         ms = ctypes.c_double()
         self._ck(lib().bnmf_sample_z(self._h, int(it), ctypes.byref(ms)))
         return ms.value
+
+
+def release_cached_memory():
+    """Hand the device blocks kept from closed handles back to the driver (bnmf_release_cached_memory)."""
+    if lib().bnmf_release_cached_memory() != 0:
+        raise BnmfError(lib().bnmf_last_error().decode())
 
 
 def comm_unique_id():

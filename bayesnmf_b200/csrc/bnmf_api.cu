@@ -159,12 +159,90 @@ static std::mutex g_pin_mutex;
 static void* g_pin = nullptr;
 static size_t g_pin_bytes = 0;
 
+// Process-wide cache of device blocks handed back by destroyed handles.  bayesNMF() builds one sampler
+// after another (a rank at a time), every one with the same few block sizes; cudaMalloc / cudaFree cost
+// 1-20 ms apiece on a device that is in use, more than the upload of the counts.  Blocks are matched by
+// (device, exact size); the cache holds at most BNMF_CACHE_MB (default 4096) and is emptied by
+// bnmf_release_cached_memory() or when an allocation fails.
+struct DevBlock { void* p; size_t bytes; int device; };
+static std::mutex g_dev_mutex;
+static std::vector<DevBlock> g_dev_cache;
+static size_t g_dev_cached = 0;
+static size_t dev_cache_limit() {
+  static const size_t v = (size_t)(getenv("BNMF_CACHE_MB") ? std::max(0LL, atoll(getenv("BNMF_CACHE_MB"))) : 4096LL) << 20;
+  return v;
+}
+static int release_cached_blocks(int device) {       // device < 0: all devices
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  int prev = 0; cudaGetDevice(&prev);
+  size_t keep = 0;
+  for (size_t i = 0; i < g_dev_cache.size(); ++i) {
+    DevBlock& b = g_dev_cache[i];
+    if (device >= 0 && b.device != device) { g_dev_cache[keep++] = b; continue; }
+    cudaSetDevice(b.device); cudaFree(b.p); g_dev_cached -= b.bytes;
+  }
+  g_dev_cache.resize(keep);
+  cudaSetDevice(prev);
+  return 0;
+}
+static cudaError_t cached_malloc(void** p, size_t bytes, int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    for (size_t i = 0; i < g_dev_cache.size(); ++i)
+      if (g_dev_cache[i].device == device && g_dev_cache[i].bytes == bytes) {
+        *p = g_dev_cache[i].p; g_dev_cached -= bytes;
+        g_dev_cache[i] = g_dev_cache.back(); g_dev_cache.pop_back();
+        return cudaSuccess;
+      }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {      // make room: give the cached blocks back to the driver, try once more
+    cudaGetLastError();
+    release_cached_blocks(device);
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+// the caller has synchronised every stream that touched the block
+static void cached_free(void* p, size_t bytes, int device) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    if (g_dev_cached + bytes <= dev_cache_limit()) {
+      g_dev_cache.push_back(DevBlock{p, bytes, device}); g_dev_cached += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+// Device scratch of one call (MAP, credible intervals, assignment): blocks in power-of-two sizes from the
+// cache, handed back -- after the stream has drained -- when the call returns, error paths included.
+struct Scratch {
+  cudaStream_t stream; int device;
+  std::vector<std::pair<void*, size_t>> v;
+  Scratch(cudaStream_t s, int dev) : stream(s), device(dev) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  template <typename X> cudaError_t get(X** p, size_t bytes) {
+    size_t r = 4096; while (r < bytes) r <<= 1;
+    void* q = nullptr;
+    const cudaError_t e = cached_malloc(&q, r, device);
+    if (e == cudaSuccess) { v.push_back({q, r}); *p = static_cast<X*>(q); }
+    return e;
+  }
+  ~Scratch() {
+    if (v.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& a : v) cached_free(a.first, a.second, device);
+  }
+};
+
 template <typename T>
 struct Sampler : bnmf_handle {
   bnmf_config cfg;
   Dev<T> d;
   cudaStream_t stream = nullptr;
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;      // device blocks of this handle (returned to the process-wide cache)
   // device arrays below 64 MiB are carved out of 64 MiB slabs (zero-filled once): a handle owns
   // ~40 arrays, and cudaMalloc costs up to a millisecond apiece when the device is in use
   struct Slab { char* base; size_t cap, used; };
@@ -195,7 +273,9 @@ struct Sampler : bnmf_handle {
   ~Sampler() override {
     cudaSetDevice(cfg.device);
     commbox.reset();
-    for (void* p : allocs) cudaFree(p);
+    if (stream) cudaStreamSynchronize(stream);
+    if (side) cudaStreamSynchronize(side);
+    for (auto& a : allocs) cached_free(a.first, a.second, cfg.device);
     if (h_metrics) cudaFreeHost(h_metrics);
     for (auto e : zev) cudaEventDestroy(e);
     for (auto e : iev) cudaEventDestroy(e);
@@ -214,16 +294,17 @@ struct Sampler : bnmf_handle {
     if (n < 1) n = 1;
     const size_t bytes = (((size_t)n * sizeof(X)) + 255) & ~(size_t)255;
     if (bytes >= SLAB_BYTES) {
-      CK(cudaMalloc((void**)p, bytes));
+      const size_t rounded = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+      CK(cached_malloc((void**)p, rounded, cfg.device));
       CK(cudaMemsetAsync(*p, 0, bytes, stream));
-      allocs.push_back(*p);
+      allocs.push_back({*p, rounded});
       return 0;
     }
     if (slabs.empty() || slabs.back().used + bytes > slabs.back().cap) {
       char* base;
-      CK(cudaMalloc((void**)&base, SLAB_BYTES));
+      CK(cached_malloc((void**)&base, SLAB_BYTES, cfg.device));
       CK(cudaMemsetAsync(base, 0, SLAB_BYTES, stream));
-      allocs.push_back(base);
+      allocs.push_back({base, SLAB_BYTES});
       slabs.push_back(Slab{base, SLAB_BYTES, 0});
     }
     *p = reinterpret_cast<X*>(slabs.back().base + slabs.back().used);
@@ -237,10 +318,14 @@ struct Sampler : bnmf_handle {
   }
   int ensure_stage(long long n) {
     if (n <= stage_len) return 0;
-    if (stage) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(stage)); for (auto& a : allocs) if (a == stage) a = nullptr; }
-    CK(cudaMalloc((void**)&stage, (size_t)n * sizeof(double)));
-    allocs.push_back(stage);
-    stage_len = n;
+    const size_t rounded = ((size_t)n * sizeof(double) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    if (stage) {
+      CK(cudaStreamSynchronize(stream));
+      for (auto& a : allocs) if (a.first == stage) { cached_free(a.first, a.second, cfg.device); a.first = nullptr; }
+    }
+    CK(cached_malloc((void**)&stage, rounded, cfg.device));
+    allocs.push_back({stage, rounded});
+    stage_len = (long long)(rounded / sizeof(double));
     return 0;
   }
   static int blocks(long long n, int t) { return (int)((n + t - 1) / t); }
@@ -556,8 +641,36 @@ struct Sampler : bnmf_handle {
     if (ty == ST_T) k_cvt_out<T><<<b, 256, 0, stream>>>((const T*)p, stage, len);
     else if (ty == ST_I32) k_cvt_out<int32_t><<<b, 256, 0, stream>>>((const int32_t*)p, stage, len);
     else k_cvt_out<unsigned long long><<<b, 256, 0, stream>>>((const unsigned long long*)p, stage, len);
-    CK(cudaMemcpyAsync(out, stage, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    const size_t bytes = (size_t)len * sizeof(double);
+    if (bytes < ((size_t)1 << 20)) {
+      CK(cudaMemcpyAsync(out, stage, bytes, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      return 0;
+    }
+    // large results (E, Mhat): DMA into the process-wide pinned buffer, then a threaded copy into the
+    // caller's pageable array (its first-touch page faults spread over the threads) -- the driver's
+    // own pageable path does both serially
+    std::lock_guard<std::mutex> pin_lock(g_pin_mutex);
+    if (g_pin_bytes < bytes) {
+      if (g_pin) cudaFreeHost(g_pin);
+      g_pin = nullptr; g_pin_bytes = 0;
+      CK(cudaMallocHost(&g_pin, bytes));
+      g_pin_bytes = bytes;
+    }
+    CK(cudaMemcpyAsync(g_pin, stage, bytes, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 8) nt = 8;
+    const size_t per = ((bytes / nt + 4095) / 4096) * 4096;
+    auto part = [&](unsigned t) {
+      const size_t lo = (size_t)t * per, hi = std::min(bytes, lo + per);
+      if (lo < hi) memcpy((char*)out + lo, (const char*)g_pin + lo, hi - lo);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(part, t);
+    part(0);
+    for (auto& t : th) t.join();
     return 0;
   }
   int get_state(const char* name, double* out, int64_t len) override {
@@ -1037,5 +1150,6 @@ int bnmf_comm_share(bnmf_handle* h, bnmf_handle* src) { NEED(h); NEED(src); retu
 int bnmf_timing(bnmf_handle* h, double* t, double* it, double* z, int64_t* l) { NEED(h); return h->timing(t, it, z, l); }
 int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes) { NEED(h); return h->set_l2_flush(bytes); }
 int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* ms) { NEED(h); return h->sample_z(iter, ms); }
+int bnmf_release_cached_memory(void) { return release_cached_blocks(-1); }
 
 }  // extern "C"

@@ -72,11 +72,12 @@ template <typename T> int Sampler<T>::get_map(int n_samples, double* P_map, doub
   if (map_slots(n_samples, match, mode)) return 1;
   const int N = cfg.N, K = cfg.K; const long long KN = (long long)K * N, NG = (long long)N * cfg.G;
   const int nm = (int)match.size();
+  Scratch sc(stream, cfg.device);
   int* dslots; double* colsum; double* outP; double* outE;
-  CK(cudaMalloc((void**)&dslots, sizeof(int) * nm));
-  CK(cudaMalloc((void**)&colsum, sizeof(double) * (size_t)nm * N));
-  CK(cudaMalloc((void**)&outP, sizeof(double) * KN));
-  CK(cudaMalloc((void**)&outE, sizeof(double) * NG));
+  CK(sc.get(&dslots, sizeof(int) * nm));
+  CK(sc.get(&colsum, sizeof(double) * (size_t)nm * N));
+  CK(sc.get(&outP, sizeof(double) * KN));
+  CK(sc.get(&outE, sizeof(double) * NG));
   CK(cudaMemcpyAsync(dslots, match.data(), sizeof(int) * nm, cudaMemcpyHostToDevice, stream));
   k_map_colsum<T><<<dim3(N, nm), 128, 0, stream>>>(d, dslots, colsum);
   k_map_mean_P<T><<<blocks(KN, 128), 128, 0, stream>>>(d, dslots, nm, colsum, outP);
@@ -85,7 +86,6 @@ template <typename T> int Sampler<T>::get_map(int n_samples, double* P_map, doub
   if (E_map) CK(cudaMemcpyAsync(E_map, outE, sizeof(double) * NG, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
-  cudaFree(dslots); cudaFree(colsum); cudaFree(outP); cudaFree(outE);
   if (A_map) for (int n = 0; n < N; ++n) A_map[n] = mode[n] == '1' ? 1.0 : 0.0;
   if (n_match_out) *n_match_out = nm;
   return 0;
@@ -159,11 +159,12 @@ template <typename T> int Sampler<T>::get_ci(int n_samples, double plo, double p
   const size_t smem = (size_t)CI_EPB * NS * sizeof(double);
   if (smem > (size_t)200 * 1024) return fail("bnmf_get_credible_intervals: %d matching samples do not fit the sort buffer", nm);
   CK(cudaFuncSetAttribute(k_ci<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  Scratch sc(stream, cfg.device);
   int* dslots; double* colsum; double* lo; double* hi;
-  CK(cudaMalloc((void**)&dslots, sizeof(int) * nm));
-  CK(cudaMalloc((void**)&colsum, sizeof(double) * (size_t)nm * N));
-  CK(cudaMalloc((void**)&lo, sizeof(double) * std::max(KN, NG)));
-  CK(cudaMalloc((void**)&hi, sizeof(double) * std::max(KN, NG)));
+  CK(sc.get(&dslots, sizeof(int) * nm));
+  CK(sc.get(&colsum, sizeof(double) * (size_t)nm * N));
+  CK(sc.get(&lo, sizeof(double) * std::max(KN, NG)));
+  CK(sc.get(&hi, sizeof(double) * std::max(KN, NG)));
   CK(cudaMemcpyAsync(dslots, match.data(), sizeof(int) * nm, cudaMemcpyHostToDevice, stream));
   k_map_colsum<T><<<dim3(N, nm), 128, 0, stream>>>(d, dslots, colsum);
   for (int side = 0; side < 2; ++side) {
@@ -176,7 +177,6 @@ template <typename T> int Sampler<T>::get_ci(int n_samples, double plo, double p
     CK(cudaStreamSynchronize(stream));
   }
   CK(cudaGetLastError());
-  cudaFree(dslots); cudaFree(colsum); cudaFree(lo); cudaFree(hi);
   if (n_match_out) *n_match_out = nm;
   return 0;
 }
@@ -255,11 +255,12 @@ template <typename T> int Sampler<T>::assign(int n_samples, const double* ref, i
   if (nk > n_ref) return fail("bnmf_assign_signatures: %d included signatures but only %d reference signatures", nk, n_ref);
   // MAP signatures (mean of the renormalised matching samples), then all cosines on the device
   const long long KN = (long long)K * N;
+  Scratch sc(stream, cfg.device);
   int* dslots; int* dkeep; double* colsum; double* dPmap; double* dref; double* dcos;
-  CK(cudaMalloc((void**)&dslots, sizeof(int) * nm)); CK(cudaMalloc((void**)&dkeep, sizeof(int) * nk));
-  CK(cudaMalloc((void**)&colsum, sizeof(double) * (size_t)nm * N)); CK(cudaMalloc((void**)&dPmap, sizeof(double) * KN));
-  CK(cudaMalloc((void**)&dref, sizeof(double) * (size_t)K * n_ref));
-  CK(cudaMalloc((void**)&dcos, sizeof(double) * (size_t)(nm + 1) * nk * n_ref));
+  CK(sc.get(&dslots, sizeof(int) * nm)); CK(sc.get(&dkeep, sizeof(int) * nk));
+  CK(sc.get(&colsum, sizeof(double) * (size_t)nm * N)); CK(sc.get(&dPmap, sizeof(double) * KN));
+  CK(sc.get(&dref, sizeof(double) * (size_t)K * n_ref));
+  CK(sc.get(&dcos, sizeof(double) * (size_t)(nm + 1) * nk * n_ref));
   CK(cudaMemcpyAsync(dslots, match.data(), sizeof(int) * nm, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(dkeep, keep.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(dref, ref, sizeof(double) * (size_t)K * n_ref, cudaMemcpyHostToDevice, stream));
@@ -270,7 +271,6 @@ template <typename T> int Sampler<T>::assign(int n_samples, const double* ref, i
   CK(cudaMemcpyAsync(cosv.data(), dcos, sizeof(double) * cosv.size(), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
-  cudaFree(dslots); cudaFree(dkeep); cudaFree(colsum); cudaFree(dPmap); cudaFree(dref); cudaFree(dcos);
   // votes: every sample's Hungarian assignment votes with its cosine (R/postprocessing.R:277-301)
   std::vector<double> V((size_t)nk * n_ref, 0.0), cost((size_t)nk * n_ref);
   std::vector<int> a;

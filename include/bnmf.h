@@ -207,6 +207,11 @@ int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes);
  * Overwrites SP / SE. */
 int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* kernel_ms);
 
+/* bnmf_destroy keeps a handle's device blocks in a process-wide cache (at most BNMF_CACHE_MB MiB,
+ * default 4096) so that the next sampler -- bayesNMF() builds one per rank, R/bayesNMF.R -- starts
+ * without allocator calls.  This hands the cached blocks of every device back to the driver. */
+int bnmf_release_cached_memory(void);
+
 #ifdef __cplusplus
 }
 #endif

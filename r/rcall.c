@@ -225,6 +225,8 @@ SEXP R_bnmf_timing(SEXP p) {
   return out;
 }
 
+SEXP R_bnmf_release_cached_memory(void) { bnmf_release_cached_memory(); return R_NilValue; }
+
 static const R_CallMethodDef calls[] = {
   {"R_bnmf_check_model", (DL_FUNC)&R_bnmf_check_model, 3}, {"R_bnmf_create", (DL_FUNC)&R_bnmf_create, 11},
   {"R_bnmf_destroy", (DL_FUNC)&R_bnmf_destroy, 1},         {"R_bnmf_set_hyper", (DL_FUNC)&R_bnmf_set_hyper, 3},
@@ -236,6 +238,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bnmf_get_sample", (DL_FUNC)&R_bnmf_get_sample, 5},   {"R_bnmf_ring_count", (DL_FUNC)&R_bnmf_ring_count, 1},
   {"R_bnmf_comm_unique_id", (DL_FUNC)&R_bnmf_comm_unique_id, 0}, {"R_bnmf_comm_init", (DL_FUNC)&R_bnmf_comm_init, 4},
   {"R_bnmf_comm_share", (DL_FUNC)&R_bnmf_comm_share, 2},   {"R_bnmf_timing", (DL_FUNC)&R_bnmf_timing, 1},
+  {"R_bnmf_release_cached_memory", (DL_FUNC)&R_bnmf_release_cached_memory, 0},
   {NULL, NULL, 0}};
 void R_init_bayesNMFb200(DllInfo* dll) {
   R_registerRoutines(dll, NULL, calls, NULL, NULL);

@@ -166,3 +166,31 @@ def test_count_limits_rejected(built_lib):
             _handle(Mb, 2)
     h = _handle(np.full((8, 4), 2.0 ** 24), 2)      # the largest supported cell
     h.close()
+
+
+@pytest.mark.parametrize("lik,prior,MH,rank", [("poisson", "gamma", False, False), ("poisson", "truncnormal", True, True), ("normal", "exponential", False, False)])
+def test_recycled_device_blocks_give_the_same_chain(built_lib, lik, prior, MH, rank):
+    """bnmf_destroy keeps a handle's device blocks for the next handle of the process (include/bnmf.h:
+    bnmf_release_cached_memory); a sampler built on blocks another chain left dirty runs the same
+    chain as one built on fresh memory."""
+    from bayesnmf_b200 import Handle, release_cached_memory
+    M, _, _ = synth_counts(96, 300, 5, 800.0, seed=3)
+
+    def chain(seed):
+        h = Handle(M.astype(np.float64), 5, likelihood=lik, prior=prior, MH=MH, learning_rank=rank, seed=seed, ring_cap=4)
+        h.init_from_prior()
+        out = h.step(5, want_P=True, want_A=True)
+        E = h.get_state("E")
+        Pm, Em, Am, nm = h.get_map(4)
+        h.close()
+        return out["metrics"], out["P"], E, Pm, Em
+
+    release_cached_memory()
+    fresh = chain(11)
+    chain(12)                       # leaves its state in the cached blocks
+    recycled = chain(11)
+    release_cached_memory()
+    again = chain(11)
+    for a, b, c in zip(fresh, recycled, again):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
