@@ -747,6 +747,7 @@ struct Sampler : bnmf_handle {
   // Overlap of the E side's hyper-draws of iteration t+1 with k_zstat of iteration t (k_eside_hyper):
   // a low-priority side stream, fork / join events, the host's copy of the iteration counter.
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_p = nullptr;
+  double* alpha_retry = nullptr; int* alpha_n_retry = nullptr; int alpha_cap = 0;   // parked Alpha_e envelopes (k_eside_hyper -> k_alpha_retry)
   bool hyper_ready = false, spec_next = false;
   int h_iter = 0;
   bool overlap_allowed() const {
@@ -774,6 +775,12 @@ struct Sampler : bnmf_handle {
                 hyper_ready = false;
               } else k_eside<T, ET, PRIOR_GAMMA, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE);
               if (spec_next && overlap_allowed()) {
+                if (!alpha_retry) {      // list of parked Alpha_e cells, a quarter of the cells long: 16 % are rejected once, an
+                                         // overflowing cell finishes in place (allocated -- zero-filled on `stream` -- before the fork)
+                  const long long ncell = (long long)cfg.N * cfg.G;
+                  alpha_cap = (int)std::max<long long>(256, std::min<long long>(ncell / 4 + 1024, 1LL << 30));
+                  if (dalloc(&alpha_retry, (long long)BNMF_ALPHA_ENV_COLS * alpha_cap) || dalloc(&alpha_n_retry, 1)) return 1;
+                }
                 CK(cudaEventRecord(ev_fork, stream));
                 CK(cudaStreamWaitEvent(side, ev_fork, 0));
                 k_pside_hyper<T, 128><<<cfg.N, 128, 0, side>>>(d, h_iter + 1);
@@ -781,9 +788,12 @@ struct Sampler : bnmf_handle {
                 {
                   static const int ht = getenv("BNMF_HYPER_THREADS") ? atoi(getenv("BNMF_HYPER_THREADS")) : 256;
                   const long long ncell = (long long)cfg.N * cfg.G;
-                  if (ht == 128) k_eside_hyper<T, 128><<<blocks(ncell, 128), 128, 0, side>>>(d, h_iter + 1);
-                  else if (ht == 512) k_eside_hyper<T, 512><<<blocks(ncell, 512), 512, 0, side>>>(d, h_iter + 1);
-                  else k_eside_hyper<T, 256><<<blocks(ncell, 256), 256, 0, side>>>(d, h_iter + 1);
+                  CK(cudaMemsetAsync(alpha_n_retry, 0, sizeof(int), side));
+                  if (ht == 128) k_eside_hyper<T, 128><<<blocks(ncell, 128), 128, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
+                  else if (ht == 512) k_eside_hyper<T, 512><<<blocks(ncell, 512), 512, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
+                  else k_eside_hyper<T, 256><<<blocks(ncell, 256), 256, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
+                  k_alpha_retry<T><<<blocks(alpha_cap, 256), 256, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
+                  ++launches;
                 }
                 CK(cudaEventRecord(ev_join, side));
                 hyper_ready = true; launches += 2;

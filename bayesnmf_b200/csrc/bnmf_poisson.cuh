@@ -164,8 +164,16 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
 // leaves idle does 3/4 of the E side's work for free (64 registers x 256 threads fit next to the
 // two k_zstat blocks of an SM).  k_eside<..., HYPER_DONE = 1> then takes the values as stored.
 // `iter` comes by value: the device's counter may already have moved on when a block starts.
+// The Alpha draw is a rejection sampler (1.19 attempts per cell): a warp that loops until its slowest
+// lane accepts runs ~2.9 passes with most lanes idle.  Here every cell makes attempt 0 in place; the
+// rejected ones (16 %) park their envelope in a global list (`retry`: 21 columns of `cap` doubles --
+// shared memory belongs to k_zstat, which runs on the same SMs) and k_alpha_retry finishes them with
+// full warps.  Attempt a of a cell reads block a of the cell's Philox stream wherever it is made, so
+// the draws are those of alpha_draw() (bnmf_rng.cuh), which the fused k_eside and the oracle use.
+#define BNMF_ALPHA_ENV_COLS 21
 template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_eside_hyper(Dev<T> d, int iter) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+k_eside_hyper(Dev<T> d, int iter, double* __restrict__ retry, int* __restrict__ n_retry, int cap) {
   const long long cells = (long long)d.N * d.G;
   const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
   const long long ii = idx < cells ? idx : cells - 1;     // the whole block runs the staged sampler (its barriers)
@@ -174,9 +182,63 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_eside_hyper(Dev<T> 
   const double be = (double)(T)gamma_draw<double>(make_stream(d.seed, iter, PUR_HYP_E1, c),
                                                   (double)d.A_e.at(ii) + al0, (double)d.B_e.at(ii) + Eold);
   __syncthreads();
-  const double al = (double)(T)alpha_draw<true>(make_stream(d.seed, iter, PUR_HYP_E2, c),
-                                                (double)d.C_e.at(ii), (double)d.D_e.at(ii), be, Eold, al0);
-  if (idx < cells) { d.Beta_e[ii] = (T)be; d.Alpha_e[ii] = (T)al; }
+  AlphaEnv e;
+  alpha_setup<true>(e, (double)d.C_e.at(ii), (double)d.D_e.at(ii), be, Eold, al0);
+  __syncthreads();
+  const Stream st = make_stream(d.seed, iter, PUR_HYP_E2, c);
+  double x = e.m;
+  bool store = idx < cells;
+  bool done = alpha_attempt(e, st, 0u, x) || idx >= cells;
+  // rejected cells take consecutive slots of the list (one atomic per warp)
+  const unsigned rej = __ballot_sync(0xffffffffu, !done);
+  if (rej) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs((int)rej) - 1) base = atomicAdd(n_retry, __popc(rej));
+    base = __shfl_sync(0xffffffffu, base, __ffs((int)rej) - 1);
+    if (!done) {
+      const int slot = base + __popc(rej & ((1u << lane) - 1u));
+      if (slot < cap) {
+        double* r = retry + slot;
+        const size_t cs = (size_t)cap;
+        r[0 * cs] = e.t.cm1; r[1 * cs] = e.t.b;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { r[(2 + q) * cs] = e.hv[q]; r[(5 + q) * cs] = e.sl[q]; r[(8 + q) * cs] = e.xs[q]; r[(15 + q) * cs] = e.mass[q]; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[(11 + q) * cs] = e.z[q];
+        r[18 * cs] = e.tot; r[19 * cs] = e.m;
+        r[20 * cs] = __longlong_as_double(ii);
+        store = false;                                    // Alpha_e[ii] is written by k_alpha_retry
+      } else {                                            // list full: finish here
+        for (uint32_t a = 1; a < BNMF_ALPHA_MAX_ATTEMPTS; ++a) if (alpha_attempt(e, st, a, x)) break;
+      }
+    }
+  }
+  if (idx < cells) d.Beta_e[ii] = (T)be;
+  if (store) d.Alpha_e[ii] = (T)x;
+}
+
+// Attempts 1, 2, ... of the cells k_eside_hyper parked, one thread per list entry.
+template <typename T>
+__global__ void __launch_bounds__(256) k_alpha_retry(Dev<T> d, int iter, const double* __restrict__ retry, const int* __restrict__ n_retry, int cap) {
+  const int n = min(*n_retry, cap);
+  const int slot = blockIdx.x * 256 + threadIdx.x;
+  if (slot >= n) return;
+  const double* r = retry + slot;
+  const size_t cs = (size_t)cap;
+  AlphaEnv e;
+  e.t.cm1 = r[0 * cs]; e.t.b = r[1 * cs];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { e.hv[q] = r[(2 + q) * cs]; e.sl[q] = r[(5 + q) * cs]; e.xs[q] = r[(8 + q) * cs]; e.mass[q] = r[(15 + q) * cs]; }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) e.z[q] = r[(11 + q) * cs];
+  e.tot = r[18 * cs]; e.m = r[19 * cs];
+  const long long ii = __double_as_longlong(r[20 * cs]);
+  const long long c = (ii % d.N) + (long long)d.N * (d.g0 + ii / d.N);
+  const Stream st = make_stream(d.seed, iter, PUR_HYP_E2, c);
+  double x = e.m;
+  for (uint32_t a = 1; a < BNMF_ALPHA_MAX_ATTEMPTS; ++a) if (alpha_attempt(e, st, a, x)) break;
+  d.Alpha_e[ii] = (T)x;
 }
 
 template <typename T, int THREADS, int PRIOR, int FROM_PRIOR, int HYPER_DONE = 0>

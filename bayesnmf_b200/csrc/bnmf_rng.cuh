@@ -275,8 +275,13 @@ BNMF_HD double seg_inv(double s, double a, double b, double q) {
 #else
 #define BNMF_STAGE() do { } while (0)
 #endif
+// Envelope of one Alpha conditional: everything an attempt of the rejection loop reads.
+struct AlphaEnv {
+  AlphaTarget t;
+  double hv[3], sl[3], xs[3], z[4], mass[3], tot, m;
+};
 template <bool STAGES = false>
-BNMF_HD_CALL double alpha_draw(const Stream st, double C, double D, double beta, double X, double x0) {
+BNMF_HD void alpha_setup(AlphaEnv& e, double C, double D, double beta, double X, double x0) {
   const double LO = 1e-3, HI = 1e4;
   AlphaTarget t; t.cm1 = C - 1.0; t.b = D - log(beta) - log(X);
   // --- approximate mode: safeguarded Newton on h' (strictly decreasing) to BNMF_ALPHA_TOL ---
@@ -338,27 +343,40 @@ BNMF_HD_CALL double alpha_draw(const Stream st, double C, double D, double beta,
   double hmax = top[0];
   if (top[1] > hmax) hmax = top[1];
   if (top[2] > hmax) hmax = top[2];
-  double mass[3], tot = 0.0;
+  double tot = 0.0;
   for (int j = 0; j < 3; ++j) {
-    mass[j] = (z[j + 1] > z[j]) ? exp(top[j] - hmax) * seg_unit(sl[j], z[j + 1] - z[j]) : 0.0;
-    tot += mass[j];
+    e.mass[j] = (z[j + 1] > z[j]) ? exp(top[j] - hmax) * seg_unit(sl[j], z[j + 1] - z[j]) : 0.0;
+    tot += e.mass[j];
   }
+  e.t = t; e.tot = tot; e.m = m;
+  for (int j = 0; j < 3; ++j) { e.hv[j] = hv[j]; e.sl[j] = sl[j]; e.xs[j] = xs[j]; }
+  for (int j = 0; j < 4; ++j) e.z[j] = z[j];
+}
+// attempt number `a` of the rejection loop: true = accepted, the draw is in x
+BNMF_HD bool alpha_attempt(const AlphaEnv& e, const Stream st, uint32_t a, double& x) {
+  U4 w = st.at(a);
+  double r = u01<double>(w.x) * e.tot;
+  int j = 0;
+  if (r >= e.mass[0]) { r -= e.mass[0]; j = 1; if (r >= e.mass[1]) { r -= e.mass[1]; j = 2; } }
+  if (!(e.mass[j] > 0.0)) return false;
+  double q = r / e.mass[j];
+  if (q >= 1.0) q = 1.0 - 1e-16;
+  double xc = seg_inv(e.sl[j], e.z[j], e.z[j + 1], q);
+  if (xc < e.z[j]) xc = e.z[j];
+  if (xc > e.z[j + 1]) xc = e.z[j + 1];
+  double env = e.hv[j] + e.sl[j] * (xc - e.xs[j]);
+  if (log(u01<double>(w.y)) <= alpha_h(e.t, xc) - env) { x = xc; return true; }
+  return false;
+}
+#define BNMF_ALPHA_MAX_ATTEMPTS 4096u
+template <bool STAGES = false>
+BNMF_HD_CALL double alpha_draw(const Stream st, double C, double D, double beta, double X, double x0) {
+  AlphaEnv e;
+  alpha_setup<STAGES>(e, C, D, beta, X, x0);
   BNMF_STAGE();
-  double x = m;
-  for (uint32_t a = 0; a < 4096u; ++a) {
-    U4 w = st.at(a);
-    double r = u01<double>(w.x) * tot;
-    int j = 0;
-    if (r >= mass[0]) { r -= mass[0]; j = 1; if (r >= mass[1]) { r -= mass[1]; j = 2; } }
-    if (!(mass[j] > 0.0)) continue;
-    double q = r / mass[j];
-    if (q >= 1.0) q = 1.0 - 1e-16;
-    double xc = seg_inv(sl[j], z[j], z[j + 1], q);
-    if (xc < z[j]) xc = z[j];
-    if (xc > z[j + 1]) xc = z[j + 1];
-    double env = hv[j] + sl[j] * (xc - xs[j]);
-    if (log(u01<double>(w.y)) <= alpha_h(t, xc) - env) { x = xc; break; }
-  }
+  double x = e.m;
+  for (uint32_t a = 0; a < BNMF_ALPHA_MAX_ATTEMPTS; ++a)
+    if (alpha_attempt(e, st, a, x)) break;
   return x;
 }
 
