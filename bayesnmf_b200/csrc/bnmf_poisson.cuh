@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) k_alpha_retry(Dev<T> d, int iter, const d
 }
 
 template <typename T, int THREADS, int PRIOR, int FROM_PRIOR, int HYPER_DONE = 0>
-__global__ void __launch_bounds__(THREADS) k_eside(Dev<T> d, int keepE) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_eside(Dev<T> d, int keepE) {
   constexpr int from_prior = FROM_PRIOR || HYPER_DONE;      // (hyper-draws already made: take them as stored)
   constexpr int prior_draw_only = FROM_PRIOR;
   __shared__ double scratch[THREADS / 32];
