@@ -779,6 +779,7 @@ struct Sampler : bnmf_handle {
                                          // overflowing cell finishes in place (allocated -- zero-filled on `stream` -- before the fork)
                   const long long ncell = (long long)cfg.N * cfg.G;
                   alpha_cap = (int)std::max<long long>(256, std::min<long long>(ncell / 4 + 1024, 1LL << 30));
+                  if (const char* e = getenv("BNMF_ALPHA_CAP")) { const int v = atoi(e); if (v >= 1) alpha_cap = v; }   // test knob (overflow path)
                   if (dalloc(&alpha_retry, (long long)BNMF_ALPHA_ENV_COLS * alpha_cap) || dalloc(&alpha_n_retry, 1)) return 1;
                 }
                 CK(cudaEventRecord(ev_fork, stream));

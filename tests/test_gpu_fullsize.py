@@ -108,3 +108,38 @@ def test_p_sweep_implementations_agree(built_lib, lik, prior, MH):
         np.testing.assert_allclose(E1, E0, rtol=rtol, atol=1e-300, err_msg=name)
         np.testing.assert_allclose(H1, H0, rtol=rtol, atol=1e-9, err_msg=name)
         np.testing.assert_allclose(m1, m0, rtol=rtol, atol=1e-7, equal_nan=True, err_msg=name)
+
+
+def test_overlapped_iterations_equal_sequential_ones(built_lib):
+    """Count matrices above 2 M cells run the hyper-draws of iteration t+1 on a side stream under the
+    latent-count kernel of iteration t (k_eside_hyper: attempt 0 of every Alpha draw in place, rejected
+    cells parked and finished by k_alpha_retry).  One call of 5 iterations (overlapped) equals 5 calls
+    of one iteration (a call's last iteration never speculates: the fused sequential kernels) bit for
+    bit; so does a run whose parking list is too short (BNMF_ALPHA_CAP: the overflow path)."""
+    from bayesnmf_b200 import Handle
+    K, G, N = 96, 24_000, 8
+    M, _, _ = synth_counts(K, G, N, 2000.0, seed=6)
+    names = ("P", "E", "Alpha_e", "Beta_e", "Alpha_p", "Beta_p", "SP", "SE")
+
+    def chain(calls, env=None):
+        os.environ.update(env or {})
+        try:
+            h = Handle(M.astype(np.float64), N, likelihood="poisson", prior="gamma", MH=False, seed=13)
+            h.init_from_prior()
+            rows = np.concatenate([h.step(n)["metrics"] for n in calls])
+        finally:
+            for k in (env or {}):
+                os.environ.pop(k, None)
+        st = {n: h.get_state(n) for n in names}
+        launches = h.timing()["launches"]
+        h.close()
+        return rows, st, launches
+
+    rows_a, st_a, l_a = chain([5])
+    rows_b, st_b, l_b = chain([1] * 5)
+    rows_c, st_c, _ = chain([5], {"BNMF_ALPHA_CAP": "16"})
+    assert l_a > l_b * 5            # the overlapped call launched the side-stream kernels, the single steps did not
+    for rows, st in ((rows_b, st_b), (rows_c, st_c)):
+        np.testing.assert_array_equal(rows_a, rows)
+        for n in names:
+            np.testing.assert_array_equal(st_a[n], st[n], err_msg=n)
