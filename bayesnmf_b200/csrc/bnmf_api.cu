@@ -191,7 +191,7 @@ static cudaError_t cached_malloc(void** p, size_t bytes, int device) {
     for (size_t i = 0; i < g_dev_cache.size(); ++i)
       if (g_dev_cache[i].device == device && g_dev_cache[i].bytes == bytes) {
         *p = g_dev_cache[i].p; g_dev_cached -= bytes;
-        g_dev_cache[i] = g_dev_cache.back(); g_dev_cache.pop_back();
+        g_dev_cache.erase(g_dev_cache.begin() + i);          // (keeps the list oldest-first)
         return cudaSuccess;
       }
   }
@@ -208,7 +208,15 @@ static void cached_free(void* p, size_t bytes, int device) {
   if (!p) return;
   {
     std::lock_guard<std::mutex> lk(g_dev_mutex);
-    if (g_dev_cached + bytes <= dev_cache_limit()) {
+    if (bytes <= dev_cache_limit()) {
+      // make room by dropping the oldest blocks (sizes nobody asked for again)
+      int prev = 0; cudaGetDevice(&prev);
+      size_t drop = 0;
+      while (g_dev_cached + bytes > dev_cache_limit() && drop < g_dev_cache.size()) {
+        DevBlock& b = g_dev_cache[drop++];
+        cudaSetDevice(b.device); cudaFree(b.p); g_dev_cached -= b.bytes;
+      }
+      if (drop) { g_dev_cache.erase(g_dev_cache.begin(), g_dev_cache.begin() + drop); cudaSetDevice(prev); }
       g_dev_cache.push_back(DevBlock{p, bytes, device}); g_dev_cached += bytes;
       return;
     }

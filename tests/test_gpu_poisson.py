@@ -1,4 +1,6 @@
 """GPU parity tests of the Poisson (non-MH) path against the oracle, through the C ABI."""
+import os
+
 import numpy as np
 import pytest
 
@@ -194,3 +196,28 @@ def test_recycled_device_blocks_give_the_same_chain(built_lib, lik, prior, MH, r
     for a, b, c in zip(fresh, recycled, again):
         np.testing.assert_array_equal(a, b)
         np.testing.assert_array_equal(a, c)
+
+
+def test_block_cache_eviction(built_lib):
+    """BNMF_CACHE_MB bounds the cache of device blocks; when it is full the oldest blocks are handed
+    back to the driver.  (The limit is read once per process: run in a child.)"""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import numpy as np
+        from tests.util import synth_counts
+        from bayesnmf_b200 import Handle
+        M, _, _ = synth_counts(96, 400, 5, 800.0, seed=3)
+        def make(seed):
+            h = Handle(M.astype(np.float64), 5, seed=seed); h.init_from_prior(); return h
+        a = make(1); ra = a.step(4)["metrics"]; a.close()          # one 64 MiB slab goes to the cache (= the limit)
+        b, c = make(2), make(3); b.step(2); c.step(2); b.close(); c.close()   # the second slab evicts the first
+        d = make(1); rd = d.step(4)["metrics"]; d.close()
+        assert np.array_equal(ra, rd)
+        print("ok")
+    """)
+    env = dict(os.environ, BNMF_CACHE_MB="64", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=env, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
