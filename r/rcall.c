@@ -12,6 +12,7 @@
  * handle is an external pointer whose finalizer calls bnmf_destroy (finalize(),
  * R/bayesNMF_sampler.R:740-745).  All calls come from the main R thread. */
 #include <stdint.h>
+#include <string.h>
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
@@ -125,6 +126,7 @@ SEXP R_bnmf_run(SEXP p, SEXP cc, SEXP post_warmup) {
   SEXP met = PROTECT(Rf_allocMatrix(REALSXP, BNMF_MC_COLS, rows));
   SEXP mm = PROTECT(Rf_allocMatrix(REALSXP, BNMF_MM_COLS, checks));
   bnmf_run_result r;
+  memset(&r, 0, sizeof r);
   int rc = bnmf_run(H(p), &c, pw, REAL(met), rows, REAL(mm), checks, &r);
   SEXP res = PROTECT(Rf_allocVector(REALSXP, 7));
   REAL(res)[0] = r.iter; REAL(res)[1] = r.converged; REAL(res)[2] = r.converged_iter; REAL(res)[3] = r.why;
