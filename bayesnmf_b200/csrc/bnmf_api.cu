@@ -801,7 +801,7 @@ struct Sampler : bnmf_handle {
                   if (ht == 128) k_eside_hyper<T, 128><<<blocks(ncell, 128), 128, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
                   else if (ht == 512) k_eside_hyper<T, 512><<<blocks(ncell, 512), 512, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
                   else k_eside_hyper<T, 256><<<blocks(ncell, 256), 256, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
-                  k_alpha_retry<T><<<blocks(alpha_cap, 256), 256, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
+                  k_alpha_retry<T><<<blocks((alpha_cap + ALPHA_RETRY_PER_WARP - 1) / ALPHA_RETRY_PER_WARP, 8), 256, 0, side>>>(d, h_iter + 1, alpha_retry, alpha_n_retry, alpha_cap);
                   ++launches;
                 }
                 CK(cudaEventRecord(ev_join, side));

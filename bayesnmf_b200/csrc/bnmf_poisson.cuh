@@ -218,27 +218,55 @@ k_eside_hyper(Dev<T> d, int iter, double* __restrict__ retry, int* __restrict__ 
   if (store) d.Alpha_e[ii] = (T)x;
 }
 
-// Attempts 1, 2, ... of the cells k_eside_hyper parked, one thread per list entry.
+// Attempts 1, 2, ... of the cells k_eside_hyper parked.  A warp owns ALPHA_RETRY_PER_WARP consecutive
+// list entries; a lane whose cell has accepted takes the warp's next entry instead of idling until the
+// slowest lane is through (a 16 % rejection rate per attempt would otherwise cost ~3 passes per warp).
+#define ALPHA_RETRY_PER_WARP 128
 template <typename T>
-__global__ void __launch_bounds__(256) k_alpha_retry(Dev<T> d, int iter, const double* __restrict__ retry, const int* __restrict__ n_retry, int cap) {
-  const int n = min(*n_retry, cap);
-  const int slot = blockIdx.x * 256 + threadIdx.x;
-  if (slot >= n) return;
+__device__ __forceinline__ void alpha_env_load(const Dev<T>& d, int iter, const double* __restrict__ retry, size_t cs, int slot,
+                                               AlphaEnv& e, long long& ii, Stream& st) {
   const double* r = retry + slot;
-  const size_t cs = (size_t)cap;
-  AlphaEnv e;
   e.t.cm1 = r[0 * cs]; e.t.b = r[1 * cs];
 #pragma unroll
   for (int q = 0; q < 3; ++q) { e.hv[q] = r[(2 + q) * cs]; e.sl[q] = r[(5 + q) * cs]; e.xs[q] = r[(8 + q) * cs]; e.mass[q] = r[(15 + q) * cs]; }
 #pragma unroll
   for (int q = 0; q < 4; ++q) e.z[q] = r[(11 + q) * cs];
   e.tot = r[18 * cs]; e.m = r[19 * cs];
-  const long long ii = __double_as_longlong(r[20 * cs]);
+  ii = __double_as_longlong(r[20 * cs]);
   const long long c = (ii % d.N) + (long long)d.N * (d.g0 + ii / d.N);
-  const Stream st = make_stream(d.seed, iter, PUR_HYP_E2, c);
-  double x = e.m;
-  for (uint32_t a = 1; a < BNMF_ALPHA_MAX_ATTEMPTS; ++a) if (alpha_attempt(e, st, a, x)) break;
-  d.Alpha_e[ii] = (T)x;
+  st = make_stream(d.seed, iter, PUR_HYP_E2, c);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_alpha_retry(Dev<T> d, int iter, const double* __restrict__ retry, const int* __restrict__ n_retry, int cap) {
+  const int n = min(*n_retry, cap);
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long w0 = (long long)warp * ALPHA_RETRY_PER_WARP;
+  if (w0 >= n) return;
+  const int w1 = (int)min((long long)n, w0 + ALPHA_RETRY_PER_WARP);
+  const size_t cs = (size_t)cap;
+  int next = (int)w0 + 32;                    // first entry nobody has taken yet (warp-uniform)
+  int slot = (int)w0 + lane;
+  bool busy = slot < w1;
+  AlphaEnv e; long long ii = 0; Stream st;
+  uint32_t a = 1;
+  double x = 0.0;
+  if (busy) { alpha_env_load<T>(d, iter, retry, cs, slot, e, ii, st); x = e.m; }
+  while (__any_sync(0xffffffffu, busy)) {
+    bool acc = false;
+    if (busy) {
+      acc = alpha_attempt(e, st, a, x) || a + 1 >= BNMF_ALPHA_MAX_ATTEMPTS;
+      ++a;
+      if (acc) d.Alpha_e[ii] = (T)x;
+    }
+    const unsigned freed = __ballot_sync(0xffffffffu, busy && acc);
+    if (busy && acc) {
+      slot = next + __popc(freed & ((1u << lane) - 1u));
+      busy = slot < w1;
+      if (busy) { alpha_env_load<T>(d, iter, retry, cs, slot, e, ii, st); x = e.m; a = 1; }
+    }
+    next += __popc(freed);
+  }
 }
 
 template <typename T, int THREADS, int PRIOR, int FROM_PRIOR, int HYPER_DONE = 0>
