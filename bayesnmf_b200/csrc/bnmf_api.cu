@@ -461,6 +461,10 @@ struct Sampler : bnmf_handle {
       }
       h_mi = static_cast<int32_t*>(g_pin);
     }
+    // the device copy of the counts exists before the pass: every chunk is uploaded as soon as it is converted
+    int32_t* mi = nullptr;
+    if (pois) { if (dalloc(&mi, KG)) return 1; }
+    std::vector<int> ch_cuda((size_t)n_ch, 0);
     {
       auto work = [&](long long c) {
         const long long g_lo = c * CH, g_hi = std::min(G, g_lo + CH);
@@ -483,6 +487,10 @@ struct Sampler : bnmf_handle {
           sum += (long double)colsum;
         }
         ch_sum[(size_t)c] = sum;
+        if (pois && ch_bad[c] < 0) {
+          const size_t off = (size_t)g_lo * K, cnt = (size_t)(g_hi - g_lo) * K;
+          ch_cuda[(size_t)c] = (int)cudaMemcpyAsync(mi + off, h_mi + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+        }
       };
       unsigned nt = std::thread::hardware_concurrency();
       if (nt < 1) nt = 1;
@@ -490,7 +498,8 @@ struct Sampler : bnmf_handle {
       if ((long long)nt > n_ch) nt = (unsigned)n_ch;
       if (KG < (1 << 20)) nt = 1;
       std::atomic<long long> next(0);
-      auto loop = [&]() { for (long long c; (c = next.fetch_add(1)) < n_ch;) work(c); };
+      const int dev = cfg.device;
+      auto loop = [&]() { cudaSetDevice(dev); for (long long c; (c = next.fetch_add(1)) < n_ch;) work(c); };
       std::vector<std::thread> th;
       for (unsigned t = 1; t < nt; ++t) th.emplace_back(loop);
       loop();
@@ -507,10 +516,7 @@ struct Sampler : bnmf_handle {
     for (long long c = 0; c < n_ch; ++c) data_sum += ch_sum[(size_t)c];
     lap("host pass over data");
     if (pois) {
-      int32_t* mi; if (dalloc(&mi, KG)) return 1;
-      lap("alloc counts");
-      CK(cudaMemcpyAsync(mi, h_mi, (size_t)KG * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-      lap("memcpy counts");
+      for (long long c = 0; c < n_ch; ++c) if (ch_cuda[(size_t)c]) return fail("bnmf_create: upload of the counts: %s", cudaGetErrorString((cudaError_t)ch_cuda[(size_t)c]));
       d.Mi = mi;
       const int nb = 296;
       double* cpart; if (dalloc(&cpart, 2 * nb)) return 1;
