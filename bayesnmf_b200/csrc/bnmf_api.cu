@@ -274,9 +274,14 @@ struct Sampler : bnmf_handle {
   double last_iter_ms = 0;
   bool time_z = true;
   double last_total_ms = 0, last_z_ms = 0; int64_t last_launches = 0;
-  bool have_temps = false;
+  bool have_temps = false; int64_t temps_cap = 0;
   std::vector<double> h_temps;                             // host copy of the temperature schedule (bnmf_run)
   std::vector<double> h_rows;                              // every sample_metrics row so far, MC_COLS each (bnmf_run's windows)
+  struct RunState {                                        // check_convergence_'s part of self$state (bnmf_run)
+    bool have_prev = false; double prev = 0.0, best = 0.0;
+    int inarow_no_change = 0, inarow_no_best = 0, inarow_na = 0, best_iter = 0;
+    bool converged = false; int why = 0, converged_iter = 0, post_done = 0;
+  } rs;
 
   ~Sampler() override {
     cudaSetDevice(cfg.device);
@@ -350,7 +355,9 @@ struct Sampler : bnmf_handle {
     cfg = *c;
     if (cfg.K < 1 || cfg.N < 1 || cfg.G < 1) return fail("bnmf_create: K, N, G must be >= 1");
     if (cfg.N > 64) return fail("bnmf_create: N = %d > 64 is not supported by this build", cfg.N);
-    if (cfg.G > 2000000000LL / (cfg.K > cfg.N ? cfg.K : cfg.N)) { /* 64-bit indexing is used throughout; fine */ }
+    // cells are addressed with 64-bit indices, but the column count of a handle and the item / block counts
+    // derived from it are ints: one handle takes at most 2^31 - 64 columns (shard larger data sets by genome)
+    if (cfg.G > 2147483583LL) return fail("bnmf_create: G = %lld columns on one handle exceeds the supported 2^31 - 65", (long long)cfg.G);
     CK(cudaSetDevice(cfg.device));
     {
       int least = 0, greatest = 0;
@@ -420,7 +427,11 @@ struct Sampler : bnmf_handle {
     while (ZR > 1 && (long long)cts * ((K + ZR - 1) / ZR) < 7LL * 148 * 16) ZR >>= 1;
     if (const char* e = getenv("BNMF_ZR")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ZR = v; }   // tuning knob
     if (ZR > KT) ZR = KT;
-    d.n_zitems = cts * n_ktiles * ((KT + ZR - 1) / ZR);
+    {
+      const long long nz = (long long)cts * n_ktiles * ((KT + ZR - 1) / ZR);
+      if (nz > 2147483647LL) return fail("bnmf_create: %lld work items exceed the supported 2^31 - 1 (K = %d, G = %lld)", nz, K, (long long)G);
+      d.n_zitems = (int)nz;
+    }
     d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, ET);
     if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + 2 * N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
         dalloc(&d.red, PC_COLS) || dalloc(&work_ctr, n_ktiles + 8) || dalloc(&nanflags, 5 * N)) return 1;
@@ -526,7 +537,7 @@ struct Sampler : bnmf_handle {
       CK(cudaStreamSynchronize(stream));
       double a = 0, b = 0;
       for (int i = 0; i < nb; ++i) { a += hc[2 * i]; b += hc[2 * i + 1]; }
-      d.ll_const = a; d.kl_const = b;
+      d.ll_const = a; d.ll_const_all = a; d.kl_const = b;
       pin_lock.unlock();                       // (the stream was synchronised above: the upload is done)
     } else {
       if (ensure_stage(KG)) return 1;
@@ -543,7 +554,7 @@ struct Sampler : bnmf_handle {
       CK(cudaStreamSynchronize(stream));
       double b = 0;
       for (int i = 0; i < nb; ++i) b += hc[2 * i + 1];
-      d.ll_const = 0.0; d.kl_const = b;
+      d.ll_const = 0.0; d.ll_const_all = 0.0; d.kl_const = b;
     }
     lap("upload + data constants");
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (z_config()) return 1; }
@@ -624,17 +635,33 @@ struct Sampler : bnmf_handle {
     long long n = (long long)rows * cols;
     long long full = hy_len[name];
     if (n != 1 && n != full) return fail("bnmf_set_hyper: '%s' must be scalar or have %lld elements (got %lld)", name, full, n);
-    T* p; if (dalloc(&p, n)) return 1;
+    // a value of the same shape as the current one overwrites it in place (repeated updates do not grow the
+    // handle; the captured graph keeps its pointer); a change of shape takes a new array from the slab
+    const bool same_shape = (it->second->is_matrix != 0) == (n != 1);
+    T* p = const_cast<T*>(it->second->p);
+    if (!same_shape) { if (dalloc(&p, n)) return 1; }
     if (ensure_stage(n)) return 1;
+    CK(cudaStreamSynchronize(stream));
+    if (side) CK(cudaStreamSynchronize(side));
     CK(cudaMemcpyAsync(stage, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
     k_cvt_in<T><<<blocks(n, 256), 256, 0, stream>>>(stage, p, n);
     CK(cudaStreamSynchronize(stream));
-    it->second->p = p; it->second->is_matrix = n != 1;
-    drop_graph();      // the captured kernels hold the old pointer
+    if (!same_shape) {
+      it->second->p = p; it->second->is_matrix = n != 1;
+      drop_graph();      // the captured kernels hold the old pointer
+    }
     return 0;
   }
   int set_state(const char* name, const double* v, int64_t len) override {
     CK(cudaSetDevice(cfg.device));
+    if (!strcmp(name, "rowsumE")) {          // the fixed-point row sums of E, e.g. summed over shards by the host
+      if (len != cfg.N) return fail("bnmf_set_state: 'rowsumE' has %d elements", cfg.N);
+      std::vector<long long> hfx(cfg.N);
+      for (int i = 0; i < cfg.N; ++i) hfx[i] = llrint(v[i] * RS_FX);
+      CK(cudaMemcpyAsync(d.rowsumE_fx, hfx.data(), sizeof(long long) * cfg.N, cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));
+      return 0;
+    }
     auto it = st.find(name);
     if (it == st.end()) return fail("bnmf_set_state: unknown or unallocated state '%s' for this model", name);
     if (len != it->second.len) return fail("bnmf_set_state: '%s' has %lld elements, got %lld", name, it->second.len, (long long)len);
@@ -704,7 +731,11 @@ struct Sampler : bnmf_handle {
   }
   int set_temps(const double* t, int64_t n) override {
     CK(cudaSetDevice(cfg.device));
-    double* p; if (dalloc(&p, n)) return 1;
+    if (n < 1) return fail("bnmf_set_temperature_schedule: empty schedule");
+    const bool reuse = have_temps && n <= temps_cap;        // a schedule that fits the current array overwrites it
+    double* p = const_cast<double*>(d.temps);
+    if (!reuse) { if (dalloc(&p, n)) return 1; temps_cap = n; }
+    CK(cudaStreamSynchronize(stream));
     CK(cudaMemcpyAsync(p, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
     d.temps = p; d.n_temps = (int)n; have_temps = true;
@@ -728,6 +759,20 @@ struct Sampler : bnmf_handle {
     int r = g_nccl.CommInitRank(&box->comm, world_, uid, rank_);
     if (r) return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
     commbox = box; comm = box->comm; world = world_; rank = rank_;
+    return sync_data_consts();
+  }
+  // -sum lgamma(M+1) over every shard, the same bits on every rank (the rank learner compares a
+  // replicated uniform with a probability formed from it: R/sample_params.R:115-165)
+  int sync_data_consts() {
+    if (world <= 1) return 0;
+    double* buf; if (dalloc(&buf, 1)) return 1;
+    CK(cudaMemcpyAsync(buf, &d.ll_const, sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (allreduce_buf(buf, 1, NCCL_FLOAT64, NCCL_SUM)) return 1;
+    double v = 0.0;
+    CK(cudaMemcpyAsync(&v, buf, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    d.ll_const_all = v;
+    drop_graph();
     return 0;
   }
   int comm_share(bnmf_handle* src) override {
@@ -735,7 +780,7 @@ struct Sampler : bnmf_handle {
       return fail("bnmf_comm_share: genome sharding is built for the Poisson latent-count models");
     if (!src->commbox) return fail("bnmf_comm_share: the source handle has no communicator");
     commbox = src->commbox; comm = commbox->comm; world = src->world; rank = src->rank;
-    return 0;
+    return sync_data_consts();
   }
   int allreduce_stats() {   // SP + rowsumE_fx (exact int64 sums)
     if (world <= 1) return 0;
@@ -901,6 +946,7 @@ struct Sampler : bnmf_handle {
     CK(cudaGetLastError());
     if (row) memcpy(row, h_metrics, sizeof(double) * MC_COLS);
     h_rows.assign(h_metrics, h_metrics + MC_COLS);
+    rs = RunState();
     return 0;
   }
   int init_sigmasq_prior();
@@ -1175,6 +1221,12 @@ int bnmf_comm_share(bnmf_handle* h, bnmf_handle* src) { NEED(h); NEED(src); retu
 int bnmf_timing(bnmf_handle* h, double* t, double* it, double* z, int64_t* l) { NEED(h); return h->timing(t, it, z, l); }
 int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes) { NEED(h); return h->set_l2_flush(bytes); }
 int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* ms) { NEED(h); return h->sample_z(iter, ms); }
-int bnmf_release_cached_memory(void) { return release_cached_blocks(-1); }
+int bnmf_release_cached_memory(void) {
+  {   // the process-wide pinned staging buffer too (no handle is inside create / get_state: the lock is free)
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    if (g_pin) { cudaFreeHost(g_pin); g_pin = nullptr; g_pin_bytes = 0; }
+  }
+  return release_cached_blocks(-1);
+}
 
 }  // extern "C"

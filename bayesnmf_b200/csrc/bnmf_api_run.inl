@@ -16,10 +16,14 @@ template <typename T> int Sampler<T>::run(const bnmf_convergence_control* cc, in
   CK(cudaStreamSynchronize(stream));
   int iter = hc.iter;
   memset(res, 0, sizeof(*res));
-  bool have_prev = false;
-  double prev = 0.0, best = 0.0;
-  int inarow_no_change = 0, inarow_no_best = 0, inarow_na = 0, best_iter = 0;
-  bool converged = false; int why = BNMF_WHY_NONE, converged_iter = 0;
+  // state$prev_MAP_metric / best_MAP_metric / inarow_* / converged live in the sampler, as in the reference
+  // (self$state, R/convergence.R:84-141): a second call on the same handle (resume, raised maxiters) carries on
+  // from the last check instead of starting at the 'first check' branch; bnmf_init_from_prior resets them
+  bool& have_prev = rs.have_prev;
+  double& prev = rs.prev; double& best = rs.best;
+  int& inarow_no_change = rs.inarow_no_change; int& inarow_no_best = rs.inarow_no_best; int& inarow_na = rs.inarow_na;
+  int& best_iter = rs.best_iter;
+  bool& converged = rs.converged; int& why = rs.why; int& converged_iter = rs.converged_iter;
   int64_t n_rows = 0, n_checks = 0;
   std::vector<double> buf;
   const double logG = std::log((double)cfg.G_total);
@@ -95,7 +99,7 @@ template <typename T> int Sampler<T>::run(const bnmf_convergence_control* cc, in
     }
   }
   if (cfg.MH) {                                 // R/bayesNMF_sampler.R:337-348
-    int done = 0;
+    int& done = rs.post_done;                   // (a handle that has made its post-warm-up iterations makes no more)
     while (done < post_warmup) {
       const int n = std::min(cc->MAP_every - iter % cc->MAP_every, post_warmup - done);
       if (advance(n, 1)) return 1;

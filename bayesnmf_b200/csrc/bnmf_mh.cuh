@@ -969,7 +969,7 @@ __device__ __forceinline__ void a_draw_block(const Dev<T>& d, int n, double l0, 
   const int K = d.K, N = d.N;
   if (threadIdx.x == 0) {
     const int iter = d.ctrl->iter;
-    if (d.likelihood == LIK_POISSON) { l0 += d.ll_const; l1 += d.ll_const; }
+    if (d.likelihood == LIK_POISSON) { l0 += d.ll_const_all; l1 += d.ll_const_all; }
     const double q = prior_prob_1((double)*d.R, N);
     const double Tm = temperature(d, iter);
     const int Aold = d.A[n];

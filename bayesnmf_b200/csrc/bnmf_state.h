@@ -61,7 +61,9 @@ template <typename T> struct Dev {
   // data
   const int32_t* Mi;        // K x G counts (Poisson)
   const T* Mr;              // K x G reals  (Normal)
-  double ll_const;          // - sum lgamma(M+1)             (Poisson)
+  double ll_const;          // - sum lgamma(M+1) over THIS shard's columns (Poisson)
+  double ll_const_all;      // the same over all shards: what the rank learner adds to its two log-likelihoods,
+                            // identical on every rank so that replicated draws of A_n cannot diverge
   double kl_const;          //   sum M' log M', M' = max(M, 1e-6)
 
   // parameters

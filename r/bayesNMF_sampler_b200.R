@@ -18,6 +18,12 @@
 .prior_id  <- c(truncnormal = 0L, exponential = 1L, gamma = 2L)
 .method_id <- c(SBFI = 0L, BFI = 1L)
 .have_bits <- c(P = 1L, E = 2L, A = 4L, Z = 8L, sigmasq = 16L)      # BNMF_HAVE_* of include/bnmf.h
+# BNMF_HAVE_PRIOR_* of include/bnmf.h: one bit per prior-parameter matrix the user supplied
+# (bits 0..4 = Mu, Sigmasq, Lambda, Alpha, Beta on the P side, bits 8..12 on the E side); a matrix
+# whose bit is clear is drawn from its hyperprior, a set bit keeps it (NA columns are still drawn:
+# init_prior_params_, R/sample_priors.R:15-141)
+.have_prior_bits <- c(Mu_p = 1L, Sigmasq_p = 2L, Lambda_p = 4L, Alpha_p = 8L, Beta_p = 16L,
+                      Mu_e = 256L, Sigmasq_e = 512L, Lambda_e = 1024L, Alpha_e = 2048L, Beta_e = 4096L)
 .state_dims <- function(self, name) {
   K <- self$dims$K; N <- self$dims$N; G <- self$dims$G
   if (name %in% c("P", "Mu_p", "Sigmasq_p", "Lambda_p", "Alpha_p", "Beta_p", "P_acceptance_rate")) c(K, N)
@@ -39,9 +45,15 @@ b200_initialize <- function(self, private, init_params, init_prior_params, seed 
   for (nm in names(self$hyperprior_params)) .Call("R_bnmf_set_hyper", private$h, nm, self$hyperprior_params[[nm]])
   .Call("R_bnmf_set_temps", private$h, as.numeric(self$temperature_schedule))
   for (nm in names(init_params))       .Call("R_bnmf_set_state", private$h, nm, init_params[[nm]])
-  for (nm in names(init_prior_params)) .Call("R_bnmf_set_state", private$h, nm, init_prior_params[[nm]])  # NA columns are drawn
+  # Normal likelihood: the reference adds the scalars alpha / beta of the sigmasq prior to init_prior_params
+  # (R/bayesNMF_sampler.R:222-230); they are hyperparameters of the handle, not state matrices
+  for (nm in intersect(names(init_prior_params), c("alpha", "beta")))
+    .Call("R_bnmf_set_hyper", private$h, nm, as.numeric(init_prior_params[[nm]]))
+  prior_mats <- intersect(names(init_prior_params), names(.have_prior_bits))
+  for (nm in prior_mats) .Call("R_bnmf_set_state", private$h, nm, init_prior_params[[nm]])  # NA columns are drawn
   have <- sum(.have_bits[intersect(names(init_params), names(.have_bits))])
-  row1 <- .Call("R_bnmf_init", private$h, as.integer(have), as.integer(length(init_prior_params) > 0))
+  have_prior <- sum(.have_prior_bits[prior_mats])
+  row1 <- .Call("R_bnmf_init", private$h, as.integer(have), as.integer(have_prior))
   b200_pull_state(self, private)
   private$record_sample()                                   # samples$P / E / A [[1]] from self$params
   b200_append_metrics(self, matrix(row1, nrow = 1))
@@ -71,9 +83,13 @@ b200_append_metrics <- function(self, rows) {
 
 # replaces the body of the while loop of run_gibbs_sampler() (R/bayesNMF_sampler.R:273-285, and
 # :340-348 with converged = TRUE): one call advances to the next MAP / convergence check
-b200_block <- function(self, private, converged = FALSE) {
+b200_block <- function(self, private, converged = FALSE, done = 0L) {
   cc <- self$specs$convergence_control
-  n <- min(cc$MAP_every - self$state$iter %% cc$MAP_every, cc$maxiters - self$state$iter)
+  # warm-up: up to the next multiple of MAP_every, never past maxiters (:268-271, :288-296); post-warm-up
+  # MH phase (:337): `done` of the post_warmup iterations have been made, state$iter is already past maxiters
+  left <- if (converged) self$specs$post_warmup - done else cc$maxiters - self$state$iter
+  n <- min(cc$MAP_every - self$state$iter %% cc$MAP_every, left)
+  if (n <= 0) return(invisible(0L))
   out <- .Call("R_bnmf_step", private$h, as.integer(n), converged, self$dims$K, self$dims$N)
   b200_append_metrics(self, t(out[[1]]))
   if (isTRUE(self$specs$save_all_samples)) for (i in seq_len(n)) {      # samples$P[[iter]], samples$A[[iter]]

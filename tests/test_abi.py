@@ -84,3 +84,15 @@ def test_r_veneer_compiles_against_stub_and_uses_exported_entries():
     used = set(re.findall(r"\b(bnmf_[a-z_0-9]+)\s*\(", open(src).read()))
     declared = set(re.findall(r"\b(bnmf_[a-z_0-9]+)\s*\(", open(os.path.join(root, "include", "bnmf.h")).read()))
     assert used and used <= declared, used - declared
+
+
+def test_have_prior_mask_of_the_r_patch_matches_the_python_binding():
+    """r/bayesNMF_sampler_b200.R builds the same bit mask as bayesnmf_b200/_lib.py (CPU-only check of
+    the file that cannot be run here: no R in the image)."""
+    from bayesnmf_b200._lib import HAVE_PRIOR
+    src = open(os.path.join(ROOT, "r", "bayesNMF_sampler_b200.R")).read()
+    m = re.search(r"\.have_prior_bits <- c\((.*?)\)", src, flags=re.S)
+    bits = {k: int(v) for k, v in re.findall(r"(\w+) = (\d+)L", m.group(1))}
+    assert bits == HAVE_PRIOR
+    assert "have_prior <- sum(.have_prior_bits[prior_mats])" in src
+    assert "as.integer(length(init_prior_params) > 0)" not in src

@@ -67,3 +67,57 @@ def test_two_gpu_shards_equal_single_gpu(built_lib, prior, learn):
         for k in ("RMSE", "KL", "loglikelihood", "logposterior"):
             np.testing.assert_allclose(p["row1"][k], row1[k], rtol=1e-10)
     np.testing.assert_array_equal(parts[0]["metrics"], parts[1]["metrics"])      # every rank returns the same rows
+
+
+@pytest.mark.parametrize("prior,world", [("gamma", 2), ("exponential", 3)])
+def test_shards_with_host_reduction_equal_single_handle(built_lib, prior, world):
+    """The 1-GPU variant of the test above (the driver's 1-GPU tier skips that one): `world` shard
+    handles of ONE process on one device, no communicator; after every iteration the host sums what
+    the NCCL exchange of bnmf_step sums -- SP (exact integers) and rowSums(E) (exact fixed point) --
+    and hands the totals back to every shard.  P, SP and the shards of E must equal the unsharded
+    run bit for bit; the additive metric partials must add up."""
+    from bayesnmf_b200 import Handle
+    from bayesnmf_b200.hyperpriors import fill_hyperprior_params
+    from bayesnmf_b200.shard import shard_bounds
+    from tests.util import synth_counts
+    K, G, N = 96, 1003, 6
+    M, _, _ = synth_counts(K, G, N, 1200.0, seed=13)
+    hyper = fill_hyperprior_params(None, prior, float(M.mean()), N)
+
+    def make(lo, hi):
+        h = Handle(M[:, lo:hi], N, likelihood="poisson", prior=prior, MH=False, seed=8, g0=lo, G_total=G)
+        for k, v in hyper.items():
+            h.set_hyper(k, v)
+        return h
+
+    whole = make(0, G)
+    bounds = [shard_bounds(G, r, world) for r in range(world)]
+    shards = [make(lo, hi) for lo, hi in bounds]
+
+    def exchange():
+        SP = sum(h.get_state("SP") for h in shards)
+        rs = sum(h.get_state("rowsumE") for h in shards)
+        for h in shards:
+            h.set_state("SP", SP)
+            h.set_state("rowsumE", rs)
+        return SP
+
+    row_w = whole.init_from_prior()
+    rows = [h.init_from_prior() for h in shards]
+    SP = exchange()
+    np.testing.assert_array_equal(SP, whole.get_state("SP"))
+    np.testing.assert_allclose(sum(r["loglikelihood"] for r in rows), row_w["loglikelihood"], rtol=1e-12)
+    for it in range(8):
+        mw = whole.step(1)["metrics"][0]
+        ms = [h.step(1)["metrics"][0] for h in shards]
+        SP = exchange()
+        np.testing.assert_array_equal(SP, whole.get_state("SP"), err_msg=f"iteration {it}: SP")
+        P = whole.get_state("P")
+        E = whole.get_state("E")
+        for h, (lo, hi) in zip(shards, bounds):
+            np.testing.assert_array_equal(h.get_state("P"), P, err_msg=f"iteration {it}: P")
+            np.testing.assert_array_equal(h.get_state("E"), E[:, lo:hi], err_msg=f"iteration {it}: E")
+        np.testing.assert_allclose(sum(m[3] for m in ms), mw[3], rtol=1e-12)                  # log-likelihood adds up
+        np.testing.assert_allclose(sum(m[2] for m in ms), mw[2], rtol=1e-9, atol=1e-6)        # so does the padded KL
+    for h in shards + [whole]:
+        h.close()

@@ -149,3 +149,49 @@ def test_sweep_parity_f32_state(built_lib, lik, prior, MH):
         np.testing.assert_allclose(h.get_state("P"), o.params["P"], rtol=1e-4, atol=1e-7, err_msg=f"iter {o.iter} P")
         np.testing.assert_allclose(h.get_state("E"), o.params["E"], rtol=1e-4, atol=1e-5, err_msg=f"iter {o.iter} E")
         np.testing.assert_allclose(met[3], om["loglikelihood"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("K,G,N,prior,what", [
+    (1536, 64, 40, "exponential", "C5-like: SBS1536 context, 18 KB columns in k_e_sweep, 40 sequential conditionals"),
+    (6, 40000, 4, "truncnormal", "row-resident P sweep over a multi-block cluster (40,000 genomes per mutation type)"),
+    (96, 4099, 15, "exponential", "ragged genome count, 15 signatures"),
+])
+def test_sweep_parity_large_shapes(built_lib, K, G, N, prior, what):
+    """Oracle parity (not GPU-vs-GPU) at the shapes where the sweep kernels change their decomposition:
+    Poisson + MH, warm-up iterations and the real accept step (converged = TRUE)."""
+    M, _, _ = synth_counts(K, G, min(N, 8), 3000.0, seed=21)
+    o, h = _pair(M, N, "poisson", prior, True, seed=31)
+    row = h.init_from_prior()
+    names = _names("poisson", prior, True)
+    _check_state(o, h, names, "init", True)
+    _check_row([row[k] for k in row], o.metrics[0], "init", True)
+    for it in range(2):
+        om = o.step()
+        met = h.step(1)["metrics"][0]
+        _check_state(o, h, names, f"{what}: iter {o.iter}", True)
+        _check_row(met, om, f"iter {o.iter}", True)
+    o.converged = True
+    for it in range(2):
+        om = o.step()
+        met = h.step(1, converged=True)["metrics"][0]
+        _check_state(o, h, names, f"{what}: MH iter {o.iter}", True)
+        _check_row(met, om, f"MH iter {o.iter}", True)
+    np.testing.assert_allclose(h.get_state("Mhat"), o.get_Mhat(), rtol=1e-9, atol=1e-9)
+    h.close()
+
+
+def test_normal_parity_c4_like(built_lib):
+    """Normal likelihood through the Gram-matrix P sweep at a C4-like shape (N = 15, thousands of genomes)."""
+    K, G, N = 96, 3001, 15
+    M, _, _ = synth_counts(K, G, 8, 3000.0, seed=22)
+    M = M + np.random.default_rng(1).normal(0, 2.0, M.shape)
+    o, h = _pair(M, N, "normal", "truncnormal", False, seed=32)
+    h.init_from_prior()
+    names = _names("normal", "truncnormal", False)
+    _check_state(o, h, names, "init", False)
+    for it in range(3):
+        om = o.step()
+        met = h.step(1)["metrics"][0]
+        _check_state(o, h, names, f"iter {o.iter}", False)
+        _check_row(met, om, f"iter {o.iter}", False)
+    h.close()
