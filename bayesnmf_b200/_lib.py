@@ -76,6 +76,7 @@ def lib():
     L.bnmf_timing.argtypes = [vp, dp, dp, dp, ctypes.POINTER(i64)]
     L.bnmf_set_l2_flush.argtypes = [vp, ctypes.c_size_t]
     L.bnmf_sample_z.argtypes = [vp, i32, dp]
+    L.bnmf_profile_iteration.argtypes = [vp, i32, ctypes.c_char_p, dp, ctypes.POINTER(i32), i32, ctypes.POINTER(i32)]
     L.bnmf_release_cached_memory.argtypes = []
     _lib = L
     return L
@@ -103,7 +104,7 @@ MAP_METRIC_NAMES = ["iter", "loglikelihood", "logposterior", "n_params", "BIC", 
 EXPORTS = ["bnmf_check_model", "bnmf_create", "bnmf_destroy", "bnmf_last_error", "bnmf_set_hyper",
            "bnmf_set_state", "bnmf_get_state", "bnmf_set_temperature_schedule", "bnmf_init_from_prior",
            "bnmf_step", "bnmf_run", "bnmf_ring_count", "bnmf_get_sample", "bnmf_get_map", "bnmf_get_credible_intervals", "bnmf_assign_signatures", "bnmf_comm_unique_id",
-           "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z",
+           "bnmf_comm_init", "bnmf_comm_share", "bnmf_timing", "bnmf_set_l2_flush", "bnmf_sample_z", "bnmf_profile_iteration",
            "bnmf_release_cached_memory"]
 
 
@@ -290,6 +291,19 @@ class Handle:
         ms = ctypes.c_double()
         self._ck(lib().bnmf_sample_z(self._h, int(it), ctypes.byref(ms)))
         return ms.value
+
+    def profile_iteration(self, converged=False, cap=64):
+        """One iteration with a CUDA event after every kernel: {kernel name: (total ms, launches)}."""
+        names = ctypes.create_string_buffer(32 * cap)
+        ms = np.zeros(cap)
+        cnt = np.zeros(cap, dtype=np.int32)
+        n = ctypes.c_int32()
+        self._ck(lib().bnmf_profile_iteration(self._h, int(bool(converged)), names, _dp(ms),
+                                              cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), cap, ctypes.byref(n)))
+        out = {}
+        for j in range(min(n.value, cap)):
+            out[names.raw[32 * j:32 * j + 32].split(b"\0")[0].decode()] = (float(ms[j]), int(cnt[j]))
+        return out
 
 
 def release_cached_memory():

@@ -95,6 +95,7 @@ struct bnmf_handle {
   virtual int timing(double* total, double* iter, double* z, int64_t* launches) = 0;
   virtual int set_l2_flush(size_t bytes) = 0;
   virtual int sample_z(int iter, double* ms) = 0;
+  virtual int profile(int converged, char* names, double* ms, int32_t* counts, int cap, int32_t* n_out) = 0;
 };
 
 template <typename T> static __global__ void k_cvt_in(const double* src, T* dst, long long n) {
@@ -597,7 +598,7 @@ struct Sampler : bnmf_handle {
     long long need = (items + ZW - 1) / ZW;
     if (bx > need) bx = (int)need;
     dim3 grid(bx, n_ktiles);
-    kern<<<grid, 32 * ZW, z_smem, stream>>>(d, make_zkeys(d.seed), KT, ZR, work_ctr);
+    kern<<<grid, 32 * ZW, z_smem, stream>>>(d, make_zkeys(d.seed), KT, ZR, work_ctr); mark("k_zstat");
     return 0;
   }
   int z_dispatch(bool configure) {
@@ -801,6 +802,62 @@ struct Sampler : bnmf_handle {
     return 0;
   }
 
+  // ---- per-kernel timing of one iteration (bnmf_profile_iteration) ---------------------
+  // mark(name) follows every kernel launch of an iteration: with profiling on it records an event on the
+  // launching stream, so that the span since the previous mark is that kernel's device time (the stream is
+  // in order and the host runs ahead of it)
+  bool prof_on = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> prof_ev;
+  std::vector<cudaEvent_t> prof_pool;
+  void mark(const char* name) {
+    if (!prof_on) return;
+    cudaEvent_t e;
+    if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    prof_ev.push_back({name, e});
+  }
+  int profile(int converged, char* names, double* ms, int32_t* counts, int cap, int32_t* n_out) override {
+    CK(cudaSetDevice(cfg.device));
+    h_converged = converged ? 1 : 0;
+    int two[2] = {converged, -1};
+    CK(cudaMemcpyAsync(&d.ctrl->converged, two, sizeof(two), cudaMemcpyHostToDevice, stream));
+    if (overlap_allowed()) {
+      Ctrl hc; CK(cudaMemcpyAsync(&hc, d.ctrl, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      h_iter = hc.iter;
+    }
+    hyper_ready = false; spec_next = false; ++h_iter;
+    if (flush_bytes) CK(cudaMemsetAsync(flush_buf, 0, flush_bytes, stream));
+    CK(cudaStreamSynchronize(stream));
+    prof_on = true; prof_ev.clear();
+    mark("(start)");
+    const int rc = launch_iteration(false, false, nullptr, nullptr);
+    prof_on = false;
+    if (rc) return 1;
+    CK(cudaMemcpyAsync(h_metrics, d.metrics, sizeof(double) * MC_COLS, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    h_rows.insert(h_rows.end(), h_metrics, h_metrics + MC_COLS);   // the chain has advanced by one iteration
+    std::vector<std::string> nm; std::vector<double> tt; std::vector<int> cc;
+    for (size_t i = 1; i < prof_ev.size(); ++i) {
+      float t = 0; CK(cudaEventElapsedTime(&t, prof_ev[i - 1].second, prof_ev[i].second));
+      size_t j = 0; while (j < nm.size() && nm[j] != prof_ev[i].first) ++j;
+      if (j == nm.size()) { nm.push_back(prof_ev[i].first); tt.push_back(0.0); cc.push_back(0); }
+      tt[j] += t; cc[j] += 1;
+    }
+    for (auto& pe : prof_ev) prof_pool.push_back(pe.second);
+    prof_ev.clear();
+    const int n = (int)std::min<size_t>(nm.size(), (size_t)(cap < 0 ? 0 : cap));
+    for (int j = 0; j < n; ++j) {
+      if (names) { snprintf(names + 32 * (size_t)j, 32, "%s", nm[j].c_str()); }
+      if (ms) ms[j] = tt[j];
+      if (counts) counts[j] = cc[j];
+    }
+    if (n_out) *n_out = (int32_t)nm.size();
+    return 0;
+  }
+
   // ---- the iteration ---------------------------------------------------------------
   int launches = 0;
   // Overlap of the E side's hyper-draws of iteration t+1 with k_zstat of iteration t (k_eside_hyper):
@@ -820,19 +877,19 @@ struct Sampler : bnmf_handle {
     // instantiated per (prior, prior draw or not): halves the code each launch has to fetch
     const int var = (cfg.prior == BNMF_GAMMA ? 2 : 0) | (from_prior ? 1 : 0);
     switch (var) {
-      case 0: k_pside<T, 128, PRIOR_EXPONENTIAL, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              k_eside<T, ET, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
-      case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              k_eside<T, ET, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
+      case 0: k_pside<T, 128, PRIOR_EXPONENTIAL, 0><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
+              k_eside<T, ET, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside"); break;
+      case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
+              k_eside<T, ET, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside"); break;
       case 2: if (hyper_ready) {          // Beta_p / Alpha_p of this iteration were drawn under the previous k_zstat
                 CK(cudaStreamWaitEvent(stream, ev_join_p, 0));
-                k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
-              } else k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP);
+                k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
+              } else k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
               if (hyper_ready) {          // ... and so were Beta_e / Alpha_e
                 CK(cudaStreamWaitEvent(stream, ev_join, 0));
-                k_eside<T, ET, PRIOR_GAMMA, 0, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE);
+                k_eside<T, ET, PRIOR_GAMMA, 0, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside");
                 hyper_ready = false;
-              } else k_eside<T, ET, PRIOR_GAMMA, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE);
+              } else k_eside<T, ET, PRIOR_GAMMA, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside");
               if (spec_next && overlap_allowed()) {
                 if (!alpha_retry) {      // list of parked Alpha_e cells, a quarter of the cells long: 16 % are rejected once, an
                                          // overflowing cell finishes in place (allocated -- zero-filled on `stream` -- before the fork)
@@ -859,11 +916,11 @@ struct Sampler : bnmf_handle {
                 hyper_ready = true; launches += 2;
               }
               break;
-      default: k_pside<T, 128, PRIOR_GAMMA, 1><<<cfg.N, 128, 0, stream>>>(d, keepP);
-               k_eside<T, ET, PRIOR_GAMMA, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); break;
+      default: k_pside<T, 128, PRIOR_GAMMA, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
+               k_eside<T, ET, PRIOR_GAMMA, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside"); break;
     }
     launches += 2;
-    if (from_prior) { k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); ++launches; }
+    if (from_prior) { k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); mark("k_init_rank"); ++launches; }
     else if (cfg.learning_rank) { if (rank_sweep()) return 1; }
     if (!(from_prior && (have & BNMF_HAVE_Z))) {
       if (z0) CK(cudaEventRecord(z0, stream));
@@ -890,7 +947,7 @@ struct Sampler : bnmf_handle {
   // read by k_pside) and this iteration's metrics row need in ONE grouped NCCL operation:
   // the payload is ~16 KB, so the cost of the exchange is its latency, paid once.
   int finish_iteration() {
-    k_reduce_partials<T, 256><<<RED_BLOCKS, 256, 0, stream>>>(d, red_slices, red_ticket); ++launches;
+    k_reduce_partials<T, 256><<<RED_BLOCKS, 256, 0, stream>>>(d, red_slices, red_ticket); mark("k_reduce_partials"); ++launches;
     if (world > 1) {
       const bool stats = cfg.likelihood == BNMF_POISSON && !cfg.MH;
       if (stats) g_nccl.GroupStart();
@@ -899,7 +956,7 @@ struct Sampler : bnmf_handle {
       if (stats) { const int r = g_nccl.GroupEnd(); if (!rc && r) rc = fail("ncclGroupEnd: %s", g_nccl.GetErrorString(r)); }
       if (rc) return 1;
     }
-    k_metrics<T><<<1, 32, 0, stream>>>(d); ++launches;
+    k_metrics<T><<<1, 32, 0, stream>>>(d); mark("k_metrics"); ++launches;
     return 0;
   }
 
@@ -965,12 +1022,12 @@ struct Sampler : bnmf_handle {
   }
   int launch_iteration(bool wantP, bool wantA, cudaEvent_t z0, cudaEvent_t z1) {
     const long long KN = (long long)cfg.K * cfg.N;
-    k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); ++launches;
+    k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); mark("k_begin_iter"); ++launches;
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (poisson_iteration(0, 0, z0, z1)) return 1; }
     else { if (mh_iteration(0, 0)) return 1; }
     if (finish_iteration()) return 1;
     if (wantP || wantA) {
-      k_hist_copy<T><<<blocks(KN, 256), 256, 0, stream>>>(d, wantP ? P_hist : nullptr, wantA ? A_hist : nullptr); ++launches;
+      k_hist_copy<T><<<blocks(KN, 256), 256, 0, stream>>>(d, wantP ? P_hist : nullptr, wantA ? A_hist : nullptr); mark("k_hist_copy"); ++launches;
     }
     return 0;
   }
@@ -1221,6 +1278,7 @@ int bnmf_comm_share(bnmf_handle* h, bnmf_handle* src) { NEED(h); NEED(src); retu
 int bnmf_timing(bnmf_handle* h, double* t, double* it, double* z, int64_t* l) { NEED(h); return h->timing(t, it, z, l); }
 int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes) { NEED(h); return h->set_l2_flush(bytes); }
 int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* ms) { NEED(h); return h->sample_z(iter, ms); }
+int bnmf_profile_iteration(bnmf_handle* h, int32_t conv, char* names, double* ms, int32_t* counts, int32_t cap, int32_t* n) { NEED(h); return h->profile(conv, names, ms, counts, cap, n); }
 int bnmf_release_cached_memory(void) {
   {   // the process-wide pinned staging buffer too (no handle is inside create / get_state: the lock is free)
     std::lock_guard<std::mutex> lk(g_pin_mutex);

@@ -115,18 +115,18 @@ template <typename T> int Sampler<T>::p_gram_launch() {
   const int K = cfg.K, N = cfg.N;
   const long long len = (long long)K * N + (long long)N * N, KG = (long long)K * cfg.G;
   const dim3 grid((unsigned)gram_chunks, (unsigned)((K + GRAM_KT - 1) / GRAM_KT));
-  k_gram_part<T><<<grid, GRAM_KT, (size_t)2 * N * GRAM_GC * sizeof(double), stream>>>(d, gram_part);
-  k_gram_fold<<<blocks(len * 32, 256), 256, 0, stream>>>(gram_part, gram_buf, len, gram_chunks);
+  k_gram_part<T><<<grid, GRAM_KT, (size_t)2 * N * GRAM_GC * sizeof(double), stream>>>(d, gram_part); mark("k_gram_part");
+  k_gram_fold<<<blocks(len * 32, 256), 256, 0, stream>>>(gram_part, gram_buf, len, gram_chunks); mark("k_gram_fold");
   constexpr int PW = 4;
-  k_p_gram<T, PW><<<(K + PW - 1) / PW, 32 * PW, (size_t)PW * N * (1 + 3 * P_PRE) * sizeof(double), stream>>>(d, gram_buf);
-  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d);
+  k_p_gram<T, PW><<<(K + PW - 1) / PW, 32 * PW, (size_t)PW * N * (1 + 3 * P_PRE) * sizeof(double), stream>>>(d, gram_buf); mark("k_p_gram");
+  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full");
   launches += 4;
   return 0;
 }
 
 template <typename T> int Sampler<T>::p_rows_launch() {
   const long long NG = (long long)cfg.N * cfg.G;
-  k_transpose_E<T><<<blocks(NG, 256), 256, 0, stream>>>(d, Et, pr_Gp); ++launches;
+  k_transpose_E<T><<<blocks(NG, 256), 256, 0, stream>>>(d, Et, pr_Gp); ++launches; mark("k_transpose_E");
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(pr_cs * cfg.K)); lc.blockDim = dim3(pr_threads); lc.dynamicSmemBytes = pr_smem; lc.stream = stream;
   cudaLaunchAttribute at[1];
@@ -134,22 +134,22 @@ template <typename T> int Sampler<T>::p_rows_launch() {
   lc.attrs = at; lc.numAttrs = 1;
   if (pr_threads == 512) CK(cudaLaunchKernelEx(&lc, k_p_rows<T, 512>, d, (const T*)Et, pr_Gp, pr_cs, pr_gslice));
   else CK(cudaLaunchKernelEx(&lc, k_p_rows<T, 256>, d, (const T*)Et, pr_Gp, pr_cs, pr_gslice));
-  ++launches;
+  ++launches; mark("k_p_rows");
   return 0;
 }
 
 template <typename T> int Sampler<T>::rank_sweep_kernels(int* pending) {
   const int N = cfg.N;
-  k_r<T><<<1, 32, 0, stream>>>(d); ++launches;
+  k_r<T><<<1, 32, 0, stream>>>(d); mark("k_r"); ++launches;
   for (int n = 0; n < N; ++n) {
     if (world <= 1) {     // nothing to exchange: the last block of the pass reduces and draws
-      k_a_pass<T, 1><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1, red_ticket + 1); ++launches;
+      k_a_pass<T, 1><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1, red_ticket + 1); mark("k_a_pass"); ++launches;
       continue;
     }
-    k_a_pass<T, 0><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1, nullptr); ++launches;
-    k_a_reduce<T><<<1, 256, 0, stream>>>(d, col_blocks, asum); ++launches;
+    k_a_pass<T, 0><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1, nullptr); mark("k_a_pass"); ++launches;
+    k_a_reduce<T><<<1, 256, 0, stream>>>(d, col_blocks, asum); mark("k_a_reduce"); ++launches;
     if (allreduce_buf(asum, 2, NCCL_FLOAT64, NCCL_SUM)) return 1;
-    k_a_draw<T, 256><<<1, 256, 0, stream>>>(d, n, asum); ++launches;
+    k_a_draw<T, 256><<<1, 256, 0, stream>>>(d, n, asum); mark("k_a_draw"); ++launches;
   }
   *pending = N - 1;
   return 0;
@@ -158,7 +158,7 @@ template <typename T> int Sampler<T>::rank_sweep_kernels(int* pending) {
 // rank learning inside the Poisson / latent-count iteration (R/sample_params.R:67-74)
 template <typename T> int Sampler<T>::rank_sweep() {
   const long long KG = (long long)cfg.K * cfg.G;
-  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); ++launches;
+  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full"); ++launches;
   int pending = -1;
   return rank_sweep_kernels(&pending);   // the pending update is dropped: Mhat is rebuilt next iteration
 }
@@ -167,36 +167,36 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
   const int K = cfg.K, N = cfg.N; const long long G = cfg.G;
   const long long KN = (long long)K * N, NG = (long long)N * G, KG = (long long)K * G;
   if (from_prior) {
-    if (!(have & BNMF_HAVE_P)) { k_prior_fill<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0); ++launches; }
-    if (!(have & BNMF_HAVE_E)) { k_prior_fill<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1); ++launches; }
-    k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); ++launches;
+    if (!(have & BNMF_HAVE_P)) { k_prior_fill<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0); mark("k_prior_fill"); ++launches; }
+    if (!(have & BNMF_HAVE_E)) { k_prior_fill<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1); mark("k_prior_fill"); ++launches; }
+    k_init_rank<T><<<1, 32, 0, stream>>>(d, (have & BNMF_HAVE_A) ? 1 : 0); mark("k_init_rank"); ++launches;
     CK(cudaMemsetAsync(d.nzP, 0, sizeof(int) * N, stream));
     CK(cudaMemsetAsync(d.nzE, 0, sizeof(int) * 2 * N, stream));
-    k_nzflags<T><<<blocks(std::max(KN, NG), 256), 256, 0, stream>>>(d); ++launches;
+    k_nzflags<T><<<blocks(std::max(KN, NG), 256), 256, 0, stream>>>(d); mark("k_nzflags"); ++launches;
     if (cfg.MH) {   // matrix(nrow, ncol) is NA-filled (R/bayesNMF_sampler.R:236-237)
       k_fill<T><<<blocks(KN, 256), 256, 0, stream>>>(d.P_acc, KN, (T)NAN);
       k_fill<T><<<blocks(NG, 256), 256, 0, stream>>>(d.E_acc, NG, (T)NAN);
       launches += 2;
     }
-    k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); ++launches;
-    k_final<T><<<col_blocks, 256, 0, stream>>>(d, -1, (have & BNMF_HAVE_SIGMASQ) ? 1 : 0); ++launches;
+    k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full"); ++launches;
+    k_final<T><<<col_blocks, 256, 0, stream>>>(d, -1, (have & BNMF_HAVE_SIGMASQ) ? 1 : 0); mark("k_final"); ++launches;
   } else {
-    k_hyper<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0);
-    k_hyper<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1);
+    k_hyper<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0); mark("k_hyper");
+    k_hyper<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1); mark("k_hyper");
     launches += 2;
-    if (!gram_buf) { k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); ++launches; }   // (the Gram-matrix P sweep rebuilds Mhat after itself)
+    if (!gram_buf) { k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full"); ++launches; }   // (the Gram-matrix P sweep rebuilds Mhat after itself)
     const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
     const size_t psm = (size_t)p_kx * p_gy * 2 * sizeof(double);
     const int dblocks = (K + 3) / 4;       // k_p_draw / k_p_accept: a warp per mutation type
     if (gram_buf) { if (p_gram_launch()) return 1; }
     else if (pr_cs) { if (p_rows_launch()) return 1; }
     else for (int n = 0; n < N; ++n) {
-      k_p_pass1<T><<<pgrid, pblock, psm, stream>>>(d, n, n ? n - 1 : -1);
-      k_p_draw<T><<<dblocks, 128, 0, stream>>>(d, n);
+      k_p_pass1<T><<<pgrid, pblock, psm, stream>>>(d, n, n ? n - 1 : -1); mark("k_p_pass1");
+      k_p_draw<T><<<dblocks, 128, 0, stream>>>(d, n); mark("k_p_draw");
       launches += 2;
       if (cfg.MH && h_converged) {
-        k_p_pass2<T><<<pgrid, pblock, psm, stream>>>(d, n);
-        k_p_accept<T><<<dblocks, 128, 0, stream>>>(d, n);
+        k_p_pass2<T><<<pgrid, pblock, psm, stream>>>(d, n); mark("k_p_pass2");
+        k_p_accept<T><<<dblocks, 128, 0, stream>>>(d, n); mark("k_p_accept");
         launches += 2;
       }
     }
@@ -206,14 +206,15 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
       if (e_lpg == 8) k_e_sweep<T, 8><<<eg, 32 * e_wpb, e_smem, stream>>>(d, np, e_stage);
       else if (e_lpg == 16) k_e_sweep<T, 16><<<eg, 32 * e_wpb, e_smem, stream>>>(d, np, e_stage);
       else k_e_sweep<T, 32><<<eg, 32 * e_wpb, e_smem, stream>>>(d, np, e_stage);
+      mark("k_e_sweep");
       ++launches;
     }
     int pending = -1;
     if (cfg.learning_rank) { if (rank_sweep_kernels(&pending)) return 1; }
-    k_final<T><<<col_blocks, 256, 0, stream>>>(d, pending, 0); ++launches;
+    k_final<T><<<col_blocks, 256, 0, stream>>>(d, pending, 0); mark("k_final"); ++launches;
   }
-  k_pprior<T, 128><<<N, 128, 0, stream>>>(d); ++launches;
-  if (d.ring_cap > 0) { k_ring_copy<T><<<std::min(1024, blocks(KN + NG, 256)), 256, 0, stream>>>(d); ++launches; }
+  k_pprior<T, 128><<<N, 128, 0, stream>>>(d); mark("k_pprior"); ++launches;
+  if (d.ring_cap > 0) { k_ring_copy<T><<<std::min(1024, blocks(KN + NG, 256)), 256, 0, stream>>>(d); mark("k_ring_copy"); ++launches; }
   CK(cudaGetLastError());
   return 0;
 }

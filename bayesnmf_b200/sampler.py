@@ -293,10 +293,13 @@ class bayesNMF_sampler:
 
 def bayesNMF(data, rank, likelihood="poisson", prior="truncnormal", rank_method="SBFI", MH=None,
              convergence_control=None, prop_temp=0.2, post_warmup=None, hyperprior_params=None,
-             init_prior_params=None, init_params=None, save_all_samples=True, seed=0, precision="f64", device=0):
+             init_prior_params=None, init_params=None, save_all_samples=True, seed=0, precision="f64", device=0,
+             devices=None):
     """bayesNMF (R/bayesNMF.R:24-138).  Returns the sampler after run_gibbs_sampler(); with
-    rank_method = "BIC" and several ranks, one fixed-rank sampler per rank is run (the
-    natural one-rank-per-GPU fan-out, :66-127) and a dict(results, best_rank, sampler) returned."""
+    rank_method = "BIC" and several ranks, one fixed-rank sampler per rank is run (:66-127) and a
+    dict(results, best_rank, sampler) returned.  `devices` = list of CUDA ordinals: the ranks of the
+    BIC range are placed one per GPU and run side by side (bayesnmf_b200/replicas.py); every rank's
+    chain is the one the serial loop would have run."""
     kw = dict(likelihood=likelihood, prior=prior, rank_method=rank_method, MH=MH, convergence_control=convergence_control,
               prop_temp=prop_temp, post_warmup=post_warmup, hyperprior_params=hyperprior_params,
               init_prior_params=init_prior_params, init_params=init_params, save_all_samples=save_all_samples,
@@ -304,8 +307,14 @@ def bayesNMF(data, rank, likelihood="poisson", prior="truncnormal", rank_method=
     ranks = np.atleast_1d(np.asarray(rank, dtype=int))
     if ranks.size > 1 and rank_method == "BIC":
         results, best = [], None
-        for k in ranks:
-            s = bayesNMF_sampler(data, int(k), **kw).run_gibbs_sampler()
+        if devices is not None and len(devices) > 1:
+            from .replicas import run_replicas
+            kw.pop("device")
+            samplers = run_replicas([(lambda device, k=int(k): bayesNMF_sampler(data, k, device=device, **kw).run_gibbs_sampler())
+                                     for k in ranks], devices)
+        else:
+            samplers = (bayesNMF_sampler(data, int(k), **kw).run_gibbs_sampler() for k in ranks)
+        for k, s in zip(ranks, samplers):
             bic = s.state["MAP_metrics"][-1]["BIC"]
             results.append(dict(rank=int(k), BIC=bic, time=s.time["total"]))
             if best is None or bic < best[0]:

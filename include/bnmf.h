@@ -207,6 +207,13 @@ int bnmf_set_l2_flush(bnmf_handle* h, size_t bytes);
  * Overwrites SP / SE. */
 int bnmf_sample_z(bnmf_handle* h, int32_t iter, double* kernel_ms);
 
+/* Measurement: advance ONE iteration (as bnmf_step(h, 1, converged, ...) would, without the CUDA-graph replay
+ * and without the side-stream overlap) with a CUDA event on the launching stream after every kernel, and
+ * return the device time per kernel name: names = cap x 32 chars, ms = total of the kernel's launches,
+ * counts = its launches; *n = distinct kernels (may exceed cap).  What bench.py's `roofline` object reads. */
+int bnmf_profile_iteration(bnmf_handle* h, int32_t converged, char* names, double* ms, int32_t* counts,
+                           int32_t cap, int32_t* n);
+
 /* bnmf_destroy keeps a handle's device blocks in a process-wide cache (at most BNMF_CACHE_MB MiB,
  * default 4096) so that the next sampler -- bayesNMF() builds one per rank, R/bayesNMF.R -- starts
  * without allocator calls.  This hands the cached blocks of every device back to the driver. */
