@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbnmf_b200.so")
+# BNMF_LIB: an experiment build of the same sources (bayesnmf_b200/build.py, `defines`); default: the product library
+LIB_PATH = os.environ.get("BNMF_LIB") or os.path.join(HERE, "libbnmf_b200.so")
 
 POISSON, NORMAL = 0, 1
 TRUNCNORMAL, EXPONENTIAL, GAMMA = 0, 1, 2

@@ -261,7 +261,7 @@ struct Sampler : bnmf_handle {
   std::map<std::string, Hyper<T>*> hy;
   std::map<std::string, long long> hy_len;
   double* stage = nullptr; long long stage_len = 0;      // device double staging
-  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96; int ZR = 32;
+  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96; int ZR = 32, ZR_B = 2, z_ctB = 0;
   double* red_slices = nullptr; unsigned* red_ticket = nullptr;
   int* nanflags = nullptr;
   T* P_hist = nullptr; int32_t* A_hist = nullptr;
@@ -408,29 +408,29 @@ struct Sampler : bnmf_handle {
     if (cfg.MH) { if (reg("P_acceptance_rate", &d.P_acc, KN) || reg("E_acceptance_rate", &d.E_acc, NG)) return 1; }
     if (cfg.MH || cfg.likelihood == BNMF_NORMAL || cfg.learning_rank) { if (reg("Mhat", &d.Mhat, KG)) return 1; }
 
-    // work decomposition of the column kernels: K is cut into equal tiles whose P tile +
-    // accumulators fit next to the per-warp threshold / histogram tables
+    // work decomposition of the latent-count kernel: every warp owns its tables (nothing block-wide)
     NP = ((N + 3) / 4) * 4; if (NP > 32) NP = ((N + 7) / 8) * 8;
-    const size_t z_budget = NP <= 32 ? (size_t)112 * 1024 : (size_t)226 * 1024;
-    // equal K tiles (a multiple of 8 rows, at most 128), as few as fit the shared-memory budget
     const int zw = NP <= 32 ? 8 : 4;
-    for (int t = (K + 127) / 128; ; ++t) {
-      KT = (((K + t - 1) / t + 7) / 8) * 8;
-      if (KT <= 8 || zstat_smem_bytes<T>(KT, NP, N, zw) <= z_budget) break;
-    }
-    z_smem = zstat_smem_bytes<T>(KT, NP, N, zw);
-    n_ktiles = (K + KT - 1) / KT;
+    z_smem = zstat_smem_bytes<T>(NP, zw);
+    KT = K; n_ktiles = 1;
     const int cts = (int)((G + 31) / 32);
-    // rows per work item: an item costs ~12k cycles of fixed latency (E tile in, SE out, the queue
-    // atomic), rows differ widely in their counts: as coarse as leaves every resident warp
-    // (148 SMs x 16) about eight items to balance with (measured at 12.5k .. 100k genomes)
-    ZR = 32;
-    while (ZR > 1 && (long long)cts * ((K + ZR - 1) / ZR) < 7LL * 148 * 16) ZR >>= 1;
-    if (const char* e = getenv("BNMF_ZR")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ZR = v; }   // tuning knob
-    if (ZR > KT) ZR = KT;
+    // rows per work item: an item costs ~12k cycles of fixed latency (E tile in, SE out), rows differ
+    // widely in their counts: as coarse as leaves every resident warp (148 SMs x 16) about eight items
+    // to balance with (measured at 12.5k .. 100k genomes)
+    // (an item also pays ~3 us of a warp's time for its E tile and its SE flush, a row ~10 us at WGS-like counts.)
+    // The last z_ctB column tiles are cut finer (ZR_B rows): the tail of a launch is one small item.
+    ZR_B = 2; if (ZR_B > K) ZR_B = K;
+    z_ctB = (int)std::min<long long>(cts / 2, (4LL * 148 * 16 + (K + ZR_B - 1) / ZR_B - 1) / ((K + ZR_B - 1) / ZR_B));
+    ZR = 16;
+    while (ZR > 1 && (long long)(cts - z_ctB) * ((K + ZR - 1) / ZR) < 4000LL) ZR >>= 1;
+    if (const char* e = getenv("BNMF_ZR")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ZR = v; }   // tuning knobs
+    if (const char* e = getenv("BNMF_ZR_B")) { const int v = atoi(e); if (v >= 1 && v <= 32) ZR_B = v; }
+    if (const char* e = getenv("BNMF_Z_CTB")) { const int v = atoi(e); if (v >= 0 && v <= cts) z_ctB = v; }
+    if (ZR > K) ZR = K;
+    if (ZR_B > ZR) ZR_B = ZR;
     {
-      const long long nz = (long long)cts * n_ktiles * ((KT + ZR - 1) / ZR);
-      if (nz > 2147483647LL) return fail("bnmf_create: %lld work items exceed the supported 2^31 - 1 (K = %d, G = %lld)", nz, K, (long long)G);
+      const long long nz = (long long)(cts - z_ctB) * ((K + ZR - 1) / ZR) + (long long)z_ctB * ((K + ZR_B - 1) / ZR_B);
+      if (nz > 2147483647LL - (1 << 20)) return fail("bnmf_create: %lld work items exceed the supported 2^31 - 1 (K = %d, G = %lld)", nz, K, (long long)G);
       d.n_zitems = (int)nz;
     }
     d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, ET);
@@ -455,11 +455,13 @@ struct Sampler : bnmf_handle {
     const long long CH = 1024;                                   // columns per chunk
     const long long n_ch = (G + CH - 1) / CH;
     std::vector<long double> ch_sum((size_t)n_ch, 0.0L);
+    std::vector<double> ch_row;                                   // [chunk][K] row totals (the order k_zstat visits the mutation types in)
     std::vector<long long> ch_bad((size_t)n_ch, -1);             // first offending cell of a chunk
     std::vector<int> ch_why((size_t)n_ch, 0);
     // counts go through a process-wide pinned staging buffer (kept between handles: a fresh 38 MB
     // vector costs more in page faults than the whole pass over the data)
     const bool pois = cfg.likelihood == BNMF_POISSON;
+    if (pois) ch_row.assign((size_t)n_ch * K, 0.0);
     std::unique_lock<std::mutex> pin_lock(g_pin_mutex, std::defer_lock);
     int32_t* h_mi = nullptr;
     if (pois) {
@@ -492,6 +494,7 @@ struct Sampler : bnmf_handle {
               if (!(v >= 0.0) || v != std::floor(v)) { if (ch_bad[c] < 0) { ch_bad[c] = i; ch_why[c] = 1; } continue; }
               if (v > 16777216.0) { if (ch_bad[c] < 0) { ch_bad[c] = i; ch_why[c] = 2; } continue; }
               h_mi[(size_t)i] = (int32_t)v;
+              ch_row[(size_t)c * K + k] += v;
             }
             colsum += v;
           }
@@ -530,6 +533,17 @@ struct Sampler : bnmf_handle {
     if (pois) {
       for (long long c = 0; c < n_ch; ++c) if (ch_cuda[(size_t)c]) return fail("bnmf_create: upload of the counts: %s", cudaGetErrorString((cudaError_t)ch_cuda[(size_t)c]));
       d.Mi = mi;
+      {   // mutation types by descending total count (ties: by index): heavy rows first, the tail of a launch is light
+        std::vector<double> rs((size_t)K, 0.0);
+        for (long long c = 0; c < n_ch; ++c) for (int k = 0; k < K; ++k) rs[k] += ch_row[(size_t)c * K + k];
+        std::vector<int32_t> ord((size_t)K);
+        for (int k = 0; k < K; ++k) ord[k] = k;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return rs[a] > rs[b]; });
+        int32_t* ko; if (dalloc(&ko, K)) return 1;
+        CK(cudaMemcpyAsync(ko, ord.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));     // (`ord` is a local)
+        d.korder = ko;
+      }
       const int nb = 296;
       double* cpart; if (dalloc(&cpart, 2 * nb)) return 1;
       k_data_consts<<<nb, 256, 0, stream>>>(mi, KG, cpart);
@@ -592,13 +606,13 @@ struct Sampler : bnmf_handle {
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg.device);
     int per_sm = NPV <= 32 ? 2 : 1;
-    int bx = dev_sms * per_sm / n_ktiles; if (bx < 1) bx = 1;
-    const long long items = (long long)((d.G + 31) / 32) * ((KT + ZR - 1) / ZR);
+    if (const char* e = getenv("BNMF_Z_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= per_sm) per_sm = v; }   // occupancy experiments
+    int bx = dev_sms * per_sm;
+    const long long items = d.n_zitems;
     constexpr int ZW = ZWarps<NPV>::value;
     long long need = (items + ZW - 1) / ZW;
     if (bx > need) bx = (int)need;
-    dim3 grid(bx, n_ktiles);
-    kern<<<grid, 32 * ZW, z_smem, stream>>>(d, make_zkeys(d.seed), KT, ZR, work_ctr); mark("k_zstat");
+    kern<<<bx, 32 * ZW, z_smem, stream>>>(d, make_zkeys(d.seed), ZR, ZR_B, (int)((d.G + 31) / 32) - z_ctB, work_ctr); mark("k_zstat");
     return 0;
   }
   int z_dispatch(bool configure) {
@@ -619,7 +633,7 @@ struct Sampler : bnmf_handle {
     return fail("k_zstat: unsupported padded signature count %d", NP);
   }
   int z_config() {
-    if (z_smem > 227 * 1024) return fail("k_zstat: %zu bytes of shared memory needed (K tile %d, N %d)", z_smem, KT, cfg.N);
+    if (z_smem > 227 * 1024) return fail("k_zstat: %zu bytes of shared memory needed (N %d)", z_smem, cfg.N);
     return z_dispatch(true);
   }
 

@@ -498,34 +498,38 @@ __device__ __forceinline__ void zstat_quad(const U4& w, uint32_t col, const ZPiv
   }
 }
 
-// shared memory of k_zstat in bytes, for a K tile of KT rows (host and device agree on it):
-// P tile | per warp { thr, hist, cont (int), E tile (T), cell descriptors } | block SP accumulators
+// shared memory of k_zstat in bytes (host and device agree on it): per warp
+// { E tile (T), thr, hist, cont (int), cell descriptors, the row of P (T) }; nothing is shared between the warps
 template <typename T> __host__ __device__ inline size_t zstat_warp_bytes(int NP) {
-  return (size_t)32 * (zthr_rows(NP) + 2 * NP) * sizeof(int) + (size_t)32 * NP * sizeof(T) + 136 * sizeof(int);
+  return (size_t)32 * (zthr_rows(NP) + 2 * NP) * sizeof(int) + (size_t)32 * NP * sizeof(T) + 136 * sizeof(int) + (size_t)NP * sizeof(T);
 }
-template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int KT, int NP, int N, int W) {
-  return (size_t)KT * NP * sizeof(T) + (size_t)W * zstat_warp_bytes<T>(NP) + (size_t)KT * N * sizeof(int);
+template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int NP, int W) {
+  return (size_t)W * zstat_warp_bytes<T>(NP);
 }
 
+// A warp is on its own from start to end: it takes work items -- ZR mutation types x 32 genomes -- from ONE global
+// queue (the ticket of the next item is drawn while the current one is processed), stages the row of P it is
+// working on in 160 bytes of its own shared memory, and adds every finished row of SP straight to global memory
+// (integer atomics, one 64-bit RED per signature and row: 6 M per launch at C3, spread over K N addresses).  No
+// block-level barrier, no K tiling: the fixed cost of a launch is one item's tail instead of one per K tile
+// (0.084 -> 0.03 ms; it is what a 12,500-genome shard of an 8-GPU run pays 8 times as dearly).  Mutation types
+// are visited in the order `korder` (descending total count, fixed at bnmf_create), so that the last items of a
+// column tile -- the tail of the launch -- are its lightest.
 template <typename T, int NP>
 __global__ void __launch_bounds__(32 * ZWarps<NP>::value, (NP <= 32 ? 2 : 1))
-k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ctr) {
-  constexpr int W = ZWarps<NP>::value;
-  constexpr int ZT = 32 * W;
+k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA, int* work_ctr) {
   constexpr int NPAD = ZPad<NP>::value;
   constexpr int TR = zthr_rows(NP);
   const int K = d.K, N = d.N, G = d.G;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  T* Psm = reinterpret_cast<T*>(smem_raw);                          // [KT][NP]
-  unsigned char* wtabs = reinterpret_cast<unsigned char*>(Psm + (size_t)KT * NP);
+  unsigned char* wtabs = smem_raw;
   T* Esm = reinterpret_cast<T*>(wtabs + (size_t)wid * zstat_warp_bytes<T>(NP));   // [NP][32 cells]  E tile of the item
   uint32_t* thr = reinterpret_cast<uint32_t*>(Esm + NP * 32);       // [TR][32 cells]  pick thresholds of the row
   int* hist = reinterpret_cast<int*>(thr) + TR * 32;                // [NP][32 cells]  counts of the item so far (its SE)
   int* cont = hist + NP * 32;                                       // [NP][32 lanes]  counts of a share's spilled first cell
-  int* spacc = reinterpret_cast<int*>(wtabs + (size_t)W * zstat_warp_bytes<T>(NP));   // [KT][N]
-  __shared__ int s_item[W];
   // cell descriptors of the current row: {first quad, picks, Philox counter words 0,1}; entry 32 = {all quads}
   int4* desc = reinterpret_cast<int4*>(cont + NP * 32);
+  T* Prow = reinterpret_cast<T*>(reinterpret_cast<int*>(desc) + 136);   // [NP]  row k of P with A folded in
   // shared-window addresses of the two tables; opaque so that they stay in registers instead of
   // being recomputed inside the (rarely taken, hence sunk-into) cell-switch branch of the pick loop
   uint32_t thr_sa = (uint32_t)__cvta_generic_to_shared(thr), desc_sa = (uint32_t)__cvta_generic_to_shared(desc);
@@ -536,55 +540,60 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ct
   for (int n = 0; n < TR; ++n) thr[n * 32 + lane] = 0xffffffffu;   // entries >= N-1 stay "never"
 #pragma unroll
   for (int n = 0; n < NP; ++n) { hist[n * 32 + lane] = 0; cont[n * 32 + lane] = 0; }
+  // signatures this lane stages of a row of P: lane, lane + 32 (excluded ones -- A_n = 0 -- as zero)
+  const bool use0 = lane < N && d.A[lane] != 0, use1 = NP > 32 && lane + 32 < N && d.A[lane + 32] != 0;
 
-  // A block starts on K tile blockIdx.y and, when that tile's queue of work items runs dry, moves on
-  // to the next one: mutation types differ widely in their counts, so tiles differ in their work.
-  const int n_ktiles = gridDim.y;
-  for (int tt = 0; tt < n_ktiles; ++tt) {
-  const int ky = (blockIdx.y + tt) % n_ktiles;
-  const int k0 = ky * KT;
-  const int krows = min(KT, K - k0);
-  // stage P (with A folded in) and clear block accumulators
-  for (int i = tid; i < KT * NP; i += ZT) {
-    int kk = i / NP, n = i - kk * NP;
-    T v = (T)0;
-    if (kk < krows && n < N && d.A[n]) v = d.P[(long long)(k0 + kk) + (long long)K * n];
-    Psm[i] = v;
-  }
-  for (int i = tid; i < KT * N; i += ZT) spacc[i] = 0;
-  __syncthreads();
-
-  const int rts = (krows + ZR - 1) / ZR;             // row sub-tiles in this k-tile
+  // column tiles [0, ctA) are cut into chunks of ZR_A mutation types, the last ones into finer chunks of ZR_B:
+  // the items handed out at the end of a launch are small, so is the time the last warp works alone
+  const int rtsA = (K + ZR_A - 1) / ZR_A, rtsB = (K + ZR_B - 1) / ZR_B;
   const int cts = (G + 31) / 32;                     // column tiles
-  const int n_items = rts * cts;
-  const int rt_tile = (KT + ZR - 1) / ZR;
-  const int rts_all = ((d.K + KT - 1) / KT) * rt_tile;           // item id stride (for zpart)
-
+  const long long nA = (long long)rtsA * ctA;
+  const long long n_items = nA + (long long)rtsB * (cts - ctA);
+  {
+    int next = 0;
+    if (lane == 0) next = atomicAdd(work_ctr, 1);
+    next = __shfl_sync(0xffffffffu, next, 0);
   for (;;) {
-    if (lane == 0) s_item[wid] = atomicAdd(&work_ctr[ky], 1);
-    __syncwarp();
-    const int item = s_item[wid];
-    __syncwarp();
+    const int item = next;
     if (item >= n_items) break;
-    const int ct = item / rts, rt = item - ct * rts;
+    if (lane == 0) next = atomicAdd(work_ctr, 1);      // the next ticket travels while this item is processed
+    const bool fine = item >= nA;
+    const int ZR = fine ? ZR_B : ZR_A, rts = fine ? rtsB : rtsA;
+    const int ct = fine ? ctA + (int)((item - nA) / rts) : item / rts;
+    const int rt = fine ? (int)((item - nA) % rts) : item - ct * rts;
     const int g = ct * 32 + lane;
     const bool valid = g < G;
     const unsigned long long cell0 = (unsigned long long)K * (unsigned long long)(d.g0 + (long long)ct * 32);
 
+    // E tile of the item (a coalesced 16-byte-chunk load + scatter was measured: slower -- 40 live registers and a
+    // 16-way bank conflict on the scatter cost more than the sector efficiency gains)
 #pragma unroll 4
     for (int n = 0; n < NP; ++n) Esm[n * 32 + lane] = (valid && n < N) ? d.E[(long long)n + (long long)N * g] : (T)0;
     double a_sse = 0.0, a_kl = 0.0, a_ll = 0.0;
     int sp_prev0 = 0, sp_prev1 = 0;     // lane n: sum over the tile's cells of hist[n][.] after the previous row
 
-    const int kk_end = min(ZR, krows - rt * ZR);
-    for (int r = 0; r < kk_end; ++r) {
-      const int kk = rt * ZR + r;
-      const int k = k0 + kk;
+    // chunk rt = the mutation types of rank rt, rt + rts, rt + 2 rts, ... in `korder` (descending total count):
+    // every chunk holds a like share of heavy and light types, so items weigh alike; heaviest row first
+    int k = d.korder[rt];
+    T p0 = use0 ? d.P[(long long)k + (long long)K * lane] : (T)0, p1 = (T)0;
+    if (NP > 32) p1 = use1 ? d.P[(long long)k + (long long)K * (lane + 32)] : (T)0;
+    for (int r = 0; r < ZR && r * rts + rt < K; ++r) {
       const int m = valid ? d.Mi[(long long)k + (long long)K * g] : 0;
+      const int k_this = k;
+      {   // row k of P into the warp's shared memory (read by every lane in phase 1); the next row's is on its way
+        if (lane < NP) Prow[lane] = p0;
+        if (NP > 32) { if (lane + 32 < NP) Prow[lane + 32] = p1; }
+        __syncwarp();
+        if ((r + 1) < ZR && (r + 1) * rts + rt < K) {
+          k = d.korder[(r + 1) * rts + rt];
+          p0 = use0 ? d.P[(long long)k + (long long)K * lane] : (T)0;
+          if (NP > 32) p1 = use1 ? d.P[(long long)k + (long long)K * (lane + 32)] : (T)0;
+        }
+      }
       // ---- phase 1: total of this lane's cell, metric partials ----
       T total = (T)0;
 #pragma unroll
-      for (int n = 0; n < NP; ++n) total = add_rn<T>(total, mul_rn<T>(Psm[kk * NP + n], Esm[n * 32 + lane]));
+      for (int n = 0; n < NP; ++n) total = add_rn<T>(total, mul_rn<T>(Prow[n], Esm[n * 32 + lane]));
       if (valid) {
         const double mh = (double)total;
         const double lam = mh > 1e-6 ? mh : 1e-6;
@@ -605,7 +614,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ct
         T acc = (T)0;
 #pragma unroll
         for (int n = 0; n < NP - 1; ++n) {
-          acc = add_rn<T>(acc, mul_rn<T>(Psm[kk * NP + n], Esm[n * 32 + lane]));
+          acc = add_rn<T>(acc, mul_rn<T>(Prow[n], Esm[n * 32 + lane]));
           thr[n * 32 + lane] = n < N - 1 ? pick_thr(mul_rn<T>(acc, scale)) : 0xffffffffu;
         }
       }
@@ -620,7 +629,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ct
       const int excl = incl - q;
       const int Tq = __shfl_sync(0xffffffffu, incl, 31);
       {
-        const unsigned long long cell = cell0 + (unsigned long long)k + (unsigned long long)((unsigned)K * (unsigned)lane);
+        const unsigned long long cell = cell0 + (unsigned long long)k_this + (unsigned long long)((unsigned)K * (unsigned)lane);
         desc[lane] = make_int4(excl, m, (int)(uint32_t)cell, (int)(uint32_t)(cell >> 32));
         if (lane == 31) desc[32].x = Tq;
       }
@@ -708,8 +717,8 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ct
         if (n < 32) { if (lane == n) mytot0 = tot; }
         else        { if (lane == n - 32) mytot1 = tot; }
       }
-      if (lane < N && mytot0 != sp_prev0) atomicAdd(&spacc[kk * N + lane], mytot0 - sp_prev0);
-      if (NP > 32 && lane + 32 < N && mytot1 != sp_prev1) atomicAdd(&spacc[kk * N + lane + 32], mytot1 - sp_prev1);
+      if (lane < N && mytot0 != sp_prev0) atomicAdd(&d.SP[(long long)k_this + (long long)K * lane], (unsigned long long)(mytot0 - sp_prev0));
+      if (NP > 32 && lane + 32 < N && mytot1 != sp_prev1) atomicAdd(&d.SP[(long long)k_this + (long long)K * (lane + 32)], (unsigned long long)(mytot1 - sp_prev1));
       sp_prev0 = mytot0; sp_prev1 = mytot1;
       __syncwarp();   // the threshold columns are rewritten by the next row
     }
@@ -723,20 +732,11 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int KT, int ZR, int* work_ct
     // per-item metric partials, fixed reduction order
     a_sse = warp_sum(a_sse); a_kl = warp_sum(a_kl); a_ll = warp_sum(a_ll);
     if (lane == 0) {
-      const long long gi = (long long)ct * rts_all + (long long)ky * rt_tile + rt;
-      double* zp = d.zpart + gi * PC_COLS;
+      double* zp = d.zpart + (long long)item * PC_COLS;
       zp[PC_SSE] = a_sse; zp[PC_KLV] = a_kl; zp[PC_LLV] = a_ll; zp[PC_LP_E] = 0.0; zp[PC_EACC] = 0.0;
     }
+    next = __shfl_sync(0xffffffffu, next, 0);
   }
-  __syncthreads();
-  for (int i = tid; i < krows * N; i += ZT) {
-    const int v = spacc[i];
-    if (v) {
-      const int kk = i / N, n = i - kk * N;
-      atomicAdd(&d.SP[(long long)(k0 + kk) + (long long)K * n], (unsigned long long)v);
-    }
-  }
-  __syncthreads();   // the P tile and the accumulators are rewritten for the next K tile
   }
 }
 
