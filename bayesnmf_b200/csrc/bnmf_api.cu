@@ -42,6 +42,7 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, /*ncclUniqueId by value (128 bytes)*/ Id128, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
@@ -58,6 +59,7 @@ static int load_nccl() {
   LD(GetUniqueId, "ncclGetUniqueId");
   LD(CommInitRank, "ncclCommInitRank");
   LD(AllReduce, "ncclAllReduce");
+  LD(AllGather, "ncclAllGather");
   LD(GroupStart, "ncclGroupStart");
   LD(GroupEnd, "ncclGroupEnd");
   LD(CommDestroy, "ncclCommDestroy");
@@ -68,9 +70,21 @@ static int load_nccl() {
 // a communicator shared by the handles of one process (chains / ranks of a BIC fan-out reuse it)
 struct CommBox {
   void* comm = nullptr;
-  ~CommBox() { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
+  // one-shot all-reduce over NVLink peer memory (k_reduce_partials): this rank's exchange buffer, the peers'
+  // buffers mapped through CUDA IPC, the number of the last exchange
+  bool xchg_ok = false; int device = 0;
+  unsigned long long* xlocal = nullptr; unsigned long long* xbuf[XCHG_MAX_WORLD] = {}; void* xopened[XCHG_MAX_WORLD] = {};
+  int slot_words = 0; unsigned long long seq = 0; int* xerr = nullptr;
+  ~CommBox() {
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(device);
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (xopened[r]) cudaIpcCloseMemHandle(xopened[r]);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);       // (a collective: every peer has stopped pulling by now)
+    if (xlocal) cudaFree(xlocal);
+    if (xerr) cudaFree(xerr);
+    cudaSetDevice(prev);
+  }
 };
-enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_INT32 = 2 };
+enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3, NCCL_INT32 = 2, NCCL_INT8 = 0 };
 
 // ---------------------------------------------------------------------------------
 struct bnmf_handle {
@@ -774,7 +788,54 @@ struct Sampler : bnmf_handle {
     int r = g_nccl.CommInitRank(&box->comm, world_, uid, rank_);
     if (r) return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
     commbox = box; comm = box->comm; world = world_; rank = rank_;
+    box->device = cfg.device;
+    if (setup_xchg()) return 1;
     return sync_data_consts();
+  }
+  // Exchange buffers of the one-shot all-reduce: allocate this rank's, hand its IPC handle round with NCCL, map
+  // the peers'.  Every rank must end up with the same answer to "is the peer path usable?" (a rank that cannot map
+  // a peer -- no NVLink / P2P between the two devices, both ranks in one process -- sends everyone back to NCCL).
+  int setup_xchg() {
+    CommBox& b = *commbox;
+    static const bool off = getenv("BNMF_XCHG") && !strcmp(getenv("BNMF_XCHG"), "0");
+    if (off || world < 2 || world > XCHG_MAX_WORLD) return 0;
+    const long long nw = (long long)cfg.K * cfg.N + cfg.N + PC_COLS;
+    b.slot_words = (int)std::max<long long>(4096, 2 * nw);
+    const size_t bytes = ((size_t)XCHG_SLOTS * world * b.slot_words + (size_t)XCHG_SLOTS * world + 64) * sizeof(unsigned long long);
+    int ok = 1;
+    if (cudaMalloc((void**)&b.xlocal, bytes) != cudaSuccess || cudaMalloc((void**)&b.xerr, sizeof(int)) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof(mine));
+    if (ok) {
+      CK(cudaMemsetAsync(b.xlocal, 0, bytes, stream));
+      CK(cudaMemsetAsync(b.xerr, 0, sizeof(int), stream));
+      if (cudaIpcGetMemHandle(&mine, b.xlocal) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char* dsend; char* drecv; int* dflag;
+    if (dalloc(&dsend, 64) || dalloc(&drecv, 64 * world) || dalloc(&dflag, 1)) return 1;
+    CK(cudaMemcpyAsync(dsend, &mine, 64, cudaMemcpyHostToDevice, stream));
+    int r = g_nccl.AllGather(dsend, drecv, 64, NCCL_INT8, comm, stream);
+    if (r) return fail("ncclAllGather(ipc handles): %s", g_nccl.GetErrorString(r));
+    std::vector<cudaIpcMemHandle_t> all(world);
+    CK(cudaMemcpyAsync(all.data(), drecv, 64 * (size_t)world, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int p = 0; p < world && ok; ++p) {
+      if (p == rank) { b.xbuf[p] = b.xlocal; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      b.xopened[p] = ptr; b.xbuf[p] = static_cast<unsigned long long*>(ptr);
+    }
+    CK(cudaMemcpyAsync(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (allreduce_buf(dflag, 1, NCCL_INT32, NCCL_MIN)) return 1;
+    int agreed = 0;
+    CK(cudaMemcpyAsync(&agreed, dflag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    b.xchg_ok = agreed == 1;
+    if (getenv("BNMF_TRACE")) fprintf(stderr, "[bnmf_comm_init] rank %d of %d: one-shot peer-memory all-reduce %s\n", rank, world, b.xchg_ok ? "on" : "off (NCCL)");
+    return 0;
+  }
+  bool xchg_usable() const {
+    return world > 1 && commbox && commbox->xchg_ok && (long long)cfg.K * cfg.N + cfg.N + PC_COLS <= commbox->slot_words;
   }
   // -sum lgamma(M+1) over every shard, the same bits on every rank (the rank learner compares a
   // replicated uniform with a probability formed from it: R/sample_params.R:115-165)
@@ -957,20 +1018,39 @@ struct Sampler : bnmf_handle {
   int p_gram_launch();
   double* asum = nullptr; double sig_alpha = 3.0, sig_beta = 3.0;
 
-  // End of an iteration.  Sharded runs sum everything the next iteration (SP, rowSums(E):
-  // read by k_pside) and this iteration's metrics row need in ONE grouped NCCL operation:
-  // the payload is ~16 KB, so the cost of the exchange is its latency, paid once.
+  // End of an iteration: one kernel folds the partials, sums over the shards and composes the metrics row.
+  // Sharded runs sum everything the next iteration (SP, rowSums(E): read by k_pside) and this iteration's
+  // metrics row need in ONE exchange of ~16 KB inside that kernel (one-shot all-reduce over NVLink peer memory,
+  // bnmf_poisson.cuh); where the peers' memory cannot be mapped, one grouped NCCL operation + k_metrics.
   int finish_iteration() {
-    k_reduce_partials<T, 256><<<RED_BLOCKS, 256, 0, stream>>>(d, red_slices, red_ticket); mark("k_reduce_partials"); ++launches;
+    Xchg x; memset(&x, 0, sizeof(x));
+    x.world = 1;
     if (world > 1) {
+      if (xchg_usable()) {
+        CommBox& b = *commbox;
+        x.world = world; x.rank = rank; x.seq = ++b.seq; x.slot_words = b.slot_words; x.err = b.xerr;
+        for (int r = 0; r < world; ++r) x.buf[r] = b.xbuf[r];
+      } else x.world = -1;                       // NCCL sums, then k_metrics
+    }
+    k_reduce_partials<T, 256><<<RED_BLOCKS, 256, 0, stream>>>(d, red_slices, red_ticket, x); mark("k_reduce_partials"); ++launches;
+    if (x.world == -1) {
       const bool stats = cfg.likelihood == BNMF_POISSON && !cfg.MH;
       if (stats) g_nccl.GroupStart();
       int rc = stats ? allreduce_stats() : 0;
       if (!rc) rc = allreduce_red();
       if (stats) { const int r = g_nccl.GroupEnd(); if (!rc && r) rc = fail("ncclGroupEnd: %s", g_nccl.GetErrorString(r)); }
       if (rc) return 1;
+      k_metrics<T><<<1, 32, 0, stream>>>(d); mark("k_metrics"); ++launches;
     }
-    k_metrics<T><<<1, 32, 0, stream>>>(d); mark("k_metrics"); ++launches;
+    return 0;
+  }
+  // a peer that never published (process gone): the exchange kernel gives up after ~4 s and says so
+  int check_xchg() {
+    if (!(world > 1 && commbox && commbox->xchg_ok)) return 0;
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, commbox->xerr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (e) return fail("cross-GPU exchange: rank %d never published (peer process gone?)", e - 1);
     return 0;
   }
 
@@ -1101,6 +1181,7 @@ struct Sampler : bnmf_handle {
       CK(cudaMemcpyAsync(h_metrics, d.metrics, sizeof(double) * MC_COLS * chunk, cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
       CK(cudaGetLastError());
+      if (check_xchg()) return 1;
       if (metrics) memcpy(metrics + (long long)done * MC_COLS, h_metrics, sizeof(double) * MC_COLS * chunk);
       if (h_rows.size() > (size_t)MC_COLS * 2000000) h_rows.erase(h_rows.begin(), h_rows.begin() + (long long)MC_COLS * 1000000);
       h_rows.insert(h_rows.end(), h_metrics, h_metrics + (size_t)MC_COLS * chunk);

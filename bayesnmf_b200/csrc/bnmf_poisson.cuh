@@ -741,15 +741,54 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
 }
 
 // ------------------------------------------------------------------------------
-// k_reduce_partials: fold per-item / per-block partials in a fixed order.
-// red[c] = sum_items zpart[.][c] + sum_blocks epart[.][c]  (+ data constants)
-// lp_P   = sum_n zpart[n_zitems + n]   (slots written by k_pside / k_pprior)
-// RED_BLOCKS blocks each fold a fixed contiguous slice; the last one to finish (ticket)
-// folds the slices in index order, so the result does not depend on scheduling.
+// End of an iteration, ONE kernel:
+//   1. fold the per-item / per-block partials in a fixed order:
+//        red[c] = sum_items zpart[.][c] + sum_blocks epart[.][c]  (+ data constants)
+//        lp_P   = sum_n zpart[n_zitems + n]   (slots written by k_pside / k_pprior)
+//      RED_BLOCKS blocks each fold a fixed contiguous slice; the last one to finish (ticket) folds the
+//      slices in index order, so the result does not depend on scheduling;
+//   2. genome-sharded runs: that last block sums SP, rowSums(E) (integers: exact) and the metric partials
+//      (doubles, in rank order: the same bits on every rank) over the GPUs of the node -- a one-shot
+//      all-reduce over NVLink peer memory (below) instead of two NCCL launches;
+//   3. it composes the sample_metrics row (R/utils.R:339-348, :412-455), records A into the ring and
+//      advances it (record_sample, R/bayesNMF_sampler.R:651-672).
+//
+// One-shot all-reduce ("push, flag, sum locally"): every rank owns an exchange buffer that its peers have mapped
+// (CUDA IPC over NVLink / NVSwitch, bnmf_comm_init); it holds, per slot, one region and one flag per source rank.
+// Exchange number `seq` uses slot seq % XCHG_SLOTS:
+//   push   the ~16 KB payload is stored into region (slot, own rank) of EVERY rank's buffer (remote stores are
+//          fire-and-forget: no round trip), then, after a block barrier, thread q publishes to rank q:
+//          flag(slot, own rank) = seq with st.release.sys (the release is cumulative over the barrier);
+//   wait   thread r spins on the LOCAL flag (slot, r) >= seq (ld.acquire.sys);
+//   sum    every thread sums its elements over the world regions of its own buffer, in rank order: integers
+//          exactly, doubles to the same bits on every rank (L1 is bypassed: the lines were written by peers).
+// A rank is at most one exchange ahead of any peer (it needs the peer's flag to finish), so a region is rewritten
+// only after its owner has summed it.  Cost: one NVLink store latency + one fence; no remote loads.
 // ------------------------------------------------------------------------------
 constexpr int RED_BLOCKS = 64;
+constexpr int XCHG_SLOTS = 4;
+constexpr int XCHG_MAX_WORLD = 8;
+struct Xchg {
+  int world, rank;                              // world <= 1: no exchange
+  unsigned long long seq;                       // number of this exchange (1, 2, ...), the same on every rank
+  unsigned long long* buf[XCHG_MAX_WORLD];      // rank r's exchange buffer as mapped into this process
+  int slot_words;                               // 8-byte words per (slot, source) region; the flags follow the regions
+  int* err;                                     // set when a peer's flag does not arrive (bnmf_step reports it)
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <typename T> __device__ void metrics_row(const Dev<T>& d);
+
 template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_reduce_partials(Dev<T> d, double* slices /*[RED_BLOCKS][PC_COLS]*/, unsigned* ticket) {
+__global__ void __launch_bounds__(THREADS) k_reduce_partials(Dev<T> d, double* slices /*[RED_BLOCKS][PC_COLS]*/, unsigned* ticket, const Xchg x) {
   __shared__ double scratch[THREADS / 32];
   __shared__ bool last;
   const long long total = (long long)d.n_zitems + d.n_eblocks;
@@ -782,15 +821,60 @@ __global__ void __launch_bounds__(THREADS) k_reduce_partials(Dev<T> d, double* s
     *d.lp_P = s;
     *ticket = 0u;
   }
+  __syncthreads();
+  if (x.world > 1) {
+    // ---- one-shot all-reduce of [SP | rowSums(E)] (K N + N integers) and red (PC_COLS doubles) ----
+    const int n_i64 = d.K * d.N + d.N, nw = n_i64 + PC_COLS;
+    const int slot = (int)(x.seq % XCHG_SLOTS);
+    const size_t region = ((size_t)slot * x.world + x.rank) * x.slot_words;            // where this rank's payload goes, in every buffer
+    const size_t flags = (size_t)XCHG_SLOTS * x.world * x.slot_words + (size_t)slot * x.world;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.SP);     // SP and rowsumE_fx are one array
+    for (int i = threadIdx.x; i < nw; i += THREADS) {
+      const unsigned long long v = i < n_i64 ? src[i] : (unsigned long long)__double_as_longlong(d.red[i - n_i64]);
+#pragma unroll
+      for (int q = 0; q < XCHG_MAX_WORLD; ++q) if (q < x.world) x.buf[q][region + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < x.world) st_release_sys(x.buf[threadIdx.x] + flags + x.rank, x.seq);
+    if (threadIdx.x < x.world) {
+      const unsigned long long* f = x.buf[x.rank] + flags + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < x.seq) {
+        __nanosleep(32);
+        if (clock64() - t0 > 8000000000LL) { atomicExch(x.err, 1 + (int)threadIdx.x); break; }    // ~4 s: a peer is gone
+      }
+    }
+    __syncthreads();
+    const unsigned long long* mine = x.buf[x.rank] + (size_t)slot * x.world * x.slot_words;
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.SP);
+    for (int i = threadIdx.x; i < nw; i += THREADS) {
+      unsigned long long v[XCHG_MAX_WORLD];
+#pragma unroll
+      for (int r = 0; r < XCHG_MAX_WORLD; ++r) v[r] = r < x.world ? __ldcg(mine + (size_t)r * x.slot_words + i) : 0ull;
+      if (i < n_i64) {
+        unsigned long long s = 0ull;
+#pragma unroll
+        for (int r = 0; r < XCHG_MAX_WORLD; ++r) s += v[r];
+        dst[i] = s;
+      } else {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) s += __longlong_as_double((long long)v[r]);
+        d.red[i - n_i64] = s;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && x.world >= 0) metrics_row<T>(d);
 }
 
 // ------------------------------------------------------------------------------
-// k_metrics: compose the sample_metrics row (R/utils.R:339-348, :412-455), record A
-// into the ring and advance it (record_sample, R/bayesNMF_sampler.R:651-672).
+// metrics_row: compose the sample_metrics row (R/utils.R:339-348, :412-455), record A
+// into the ring and advance it (record_sample, R/bayesNMF_sampler.R:651-672).  One thread.
+// (k_metrics: the same as a kernel of its own, after an NCCL exchange.)
 // ------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_metrics(Dev<T> d) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void metrics_row(const Dev<T>& d) {
   Ctrl* c = d.ctrl;
   const int row = c->row;
   int rank = 0;
@@ -823,6 +907,11 @@ __global__ void k_metrics(Dev<T> d) {
     c->ring_pos = (c->ring_pos + 1) % d.ring_cap;
     if (c->ring_count < d.ring_cap) c->ring_count += 1;
   }
+}
+template <typename T>
+__global__ void k_metrics(Dev<T> d) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  metrics_row<T>(d);
 }
 
 }  // namespace bnmf

@@ -12,10 +12,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out_dir, prior, learn):
+def _worker(rank, world, port, out_dir, prior, learn, xchg="1"):
     import torch
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    # BNMF_XCHG=0: the per-iteration sums through NCCL; default: the one-shot all-reduce over NVLink peer memory
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), BNMF_XCHG=xchg)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from bayesnmf_b200.shard import shard_bounds, sharded_handle
@@ -37,8 +38,9 @@ def _worker(rank, world, port, out_dir, prior, learn):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("xchg", ["1", "0"])
 @pytest.mark.parametrize("prior,learn", [("gamma", False), ("exponential", True)])
-def test_two_gpu_shards_equal_single_gpu(built_lib, prior, learn):
+def test_two_gpu_shards_equal_single_gpu(built_lib, prior, learn, xchg):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -48,7 +50,7 @@ def test_two_gpu_shards_equal_single_gpu(built_lib, prior, learn):
     from tests.util import synth_counts
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(2, port, d, prior, learn), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, port, d, prior, learn, xchg), nprocs=2, join=True)
         parts = [pickle.load(open(os.path.join(d, f"r{r}.pkl"), "rb")) for r in range(2)]
     M, _, _ = synth_counts(96, 1000, 6, 1200.0, seed=13)
     h = Handle(M, 6, likelihood="poisson", prior=prior, MH=False, seed=8, learning_rank=learn)
