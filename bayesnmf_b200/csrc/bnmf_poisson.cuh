@@ -557,10 +557,15 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
     const int item = next;
     if (item >= n_items) break;
     if (lane == 0) next = atomicAdd(work_ctr, 1);      // the next ticket travels while this item is processed
+    // items in chunk-major order: chunk 0 (it holds the heaviest mutation types) of every column tile first, the
+    // lightest chunk last -- longest processing time first, the warps that finish last are on the cheapest items
+    // (a single row of the heaviest type over 32 genomes is ~8 rows' worth of picks: taken late it IS the tail)
     const bool fine = item >= nA;
     const int ZR = fine ? ZR_B : ZR_A, rts = fine ? rtsB : rtsA;
-    const int ct = fine ? ctA + (int)((item - nA) / rts) : item / rts;
-    const int rt = fine ? (int)((item - nA) % rts) : item - ct * rts;
+    const int ctn = fine ? cts - ctA : ctA;
+    const int j = fine ? (int)(item - nA) : item;
+    const int rt = j / ctn;
+    const int ct = (fine ? ctA : 0) + (j - rt * ctn);
     const int g = ct * 32 + lane;
     const bool valid = g < G;
     const unsigned long long cell0 = (unsigned long long)K * (unsigned long long)(d.g0 + (long long)ct * 32);
