@@ -21,6 +21,7 @@
 #include "bnmf_init.cuh"
 #include "bnmf_mh.cuh"
 #include "bnmf_poisson.cuh"
+#include "bnmf_tc.cuh"
 #include "bnmf_state.h"
 
 using namespace bnmf;
@@ -1016,6 +1017,8 @@ struct Sampler : bnmf_handle {
   int p_rows_launch();
   double* gram_part = nullptr; double* gram_buf = nullptr; int gram_chunks = 0;   // Normal likelihood: Gram-matrix P sweep
   int p_gram_launch();
+  int mhat_rebuild();
+  unsigned char* tc_Pd = nullptr; int* tc_eP = nullptr; size_t tc_smem = 0;     // tensor-core Mhat (Normal likelihood): digit planes of P
   double* asum = nullptr; double sig_alpha = 3.0, sig_beta = 3.0;
 
   // End of an iteration: one kernel folds the partials, sums over the shards and composes the metrics row.

@@ -66,6 +66,12 @@ template <typename T> int Sampler<T>::mh_setup() {
     const long long len = (long long)K * N + (long long)N * N;
     if (dalloc(&gram_part, (long long)gram_chunks * len) || dalloc(&gram_buf, len)) return 1;
   }
+  // Normal likelihood: Mhat on the tensor cores
+  if (cfg.likelihood == BNMF_NORMAL && N <= TC_MAX_N && !(getenv("BNMF_TC") && atoi(getenv("BNMF_TC")) == 0)) {
+    tc_smem = tc_smem_bytes<T>(N);
+    CK(cudaFuncSetAttribute(k_mhat_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    if (dalloc(&tc_Pd, (long long)tc_planes_bytes(K, N)) || dalloc(&tc_eP, K)) return 1;
+  }
   // Row-resident P sweep: a cluster of CS blocks per mutation type keeps the row of M and Mhat in
   // shared memory.  CS is the cluster size that needs the fewest waves of clusters over the K rows
   // (ties: the smaller slice per block); BNMF_P_ROWS=0 keeps the pass-per-signature kernels.
@@ -110,6 +116,22 @@ template <typename T> int Sampler<T>::mh_setup() {
   return 0;
 }
 
+// Mhat = P diag(A) E from scratch.  Normal likelihood: on the tensor cores (k_mhat_tc, bnmf_tc.cuh: tcgen05.mma on
+// exact 8-bit digit planes, error bounded absolutely -- what the residuals M - Mhat of the Normal conditionals
+// need); the Poisson models take log(Mhat) and divide by it cell by cell and keep the fp64 kernel.  BNMF_TC=0: fp64.
+template <typename T> int Sampler<T>::mhat_rebuild() {
+  const long long KG = (long long)cfg.K * cfg.G;
+  if (tc_Pd) {
+    const dim3 grid((unsigned)((cfg.G + TC_N - 1) / TC_N), (unsigned)((cfg.K + TC_M - 1) / TC_M));
+    k_tc_prep_P<T><<<grid.y, 128, 0, stream>>>(d.P, d.A, tc_Pd, tc_eP, cfg.K, cfg.N); mark("k_tc_prep_P");
+    k_mhat_tc<T><<<grid, 128, tc_smem, stream>>>(tc_Pd, tc_eP, d.E, d.Mhat, cfg.K, cfg.N, (long long)cfg.G); mark("k_mhat_tc");
+    launches += 2;
+    return 0;
+  }
+  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full"); ++launches;
+  return 0;
+}
+
 // P sweep of the Normal likelihood: Gram matrices, the chain per mutation type, Mhat rebuilt
 template <typename T> int Sampler<T>::p_gram_launch() {
   const int K = cfg.K, N = cfg.N;
@@ -119,9 +141,8 @@ template <typename T> int Sampler<T>::p_gram_launch() {
   k_gram_fold<<<blocks(len * 32, 256), 256, 0, stream>>>(gram_part, gram_buf, len, gram_chunks); mark("k_gram_fold");
   constexpr int PW = 4;
   k_p_gram<T, PW><<<(K + PW - 1) / PW, 32 * PW, (size_t)PW * N * (1 + 3 * P_PRE) * sizeof(double), stream>>>(d, gram_buf); mark("k_p_gram");
-  k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full");
-  launches += 4;
-  return 0;
+  launches += 3;
+  return mhat_rebuild();
 }
 
 template <typename T> int Sampler<T>::p_rows_launch() {
@@ -178,13 +199,13 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
       k_fill<T><<<blocks(NG, 256), 256, 0, stream>>>(d.E_acc, NG, (T)NAN);
       launches += 2;
     }
-    k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full"); ++launches;
+    if (mhat_rebuild()) return 1;
     k_final<T><<<col_blocks, 256, 0, stream>>>(d, -1, (have & BNMF_HAVE_SIGMASQ) ? 1 : 0); mark("k_final"); ++launches;
   } else {
     k_hyper<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0); mark("k_hyper");
     k_hyper<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1); mark("k_hyper");
     launches += 2;
-    if (!gram_buf) { k_mhat_full<T><<<blocks(KG, 256), 256, 0, stream>>>(d); mark("k_mhat_full"); ++launches; }   // (the Gram-matrix P sweep rebuilds Mhat after itself)
+    if (!gram_buf) { if (mhat_rebuild()) return 1; }   // (the Gram-matrix P sweep rebuilds Mhat after itself)
     const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
     const size_t psm = (size_t)p_kx * p_gy * 2 * sizeof(double);
     const int dblocks = (K + 3) / 4;       // k_p_draw / k_p_accept: a warp per mutation type

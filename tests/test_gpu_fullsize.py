@@ -99,14 +99,18 @@ def test_p_sweep_implementations_agree(built_lib, lik, prior, MH):
         res[name] = (h.get_state("P"), h.get_state("E"), h.get_state("Mhat"), out["metrics"][-1], h.timing()["launches"])
         h.close()
     assert res["rows"][4] < res["passes"][4]                   # the cluster kernel replaced 2N (4N) launches
-    for name, rtol in (("rows", 1e-9), ("gram", 1e-7)):
+    # Normal likelihood: Mhat is rebuilt on the tensor cores from inputs rounded to 32-bit fixed point
+    # (csrc/bnmf_tc.cuh): a last-bit difference between two variants can move a rounding, i.e. Mhat by
+    # N 2^-32 x (row scale of P) x (column scale of E) -- the variants agree to the north star's 1e-6, not to 1e-9
+    tc = lik == "normal"
+    for name, rtol in (("rows", 1e-6 if tc else 1e-9), ("gram", 1e-6 if tc else 1e-7)):
         if name not in res:
             continue
         P1, E1, H1, m1, _ = res[name]
         P0, E0, H0, m0, _ = res["passes"]
         np.testing.assert_allclose(P1, P0, rtol=rtol, atol=1e-300, err_msg=name)
         np.testing.assert_allclose(E1, E0, rtol=rtol, atol=1e-300, err_msg=name)
-        np.testing.assert_allclose(H1, H0, rtol=rtol, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(H1, H0, rtol=rtol, atol=1e-5 if tc else 1e-9, err_msg=name)
         np.testing.assert_allclose(m1, m0, rtol=rtol, atol=1e-7, equal_nan=True, err_msg=name)
 
 
