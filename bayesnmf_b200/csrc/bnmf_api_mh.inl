@@ -66,6 +66,11 @@ template <typename T> int Sampler<T>::mh_setup() {
     const long long len = (long long)K * N + (long long)N * N;
     if (dalloc(&gram_part, (long long)gram_chunks * len) || dalloc(&gram_buf, len)) return 1;
   }
+  // Normal likelihood: the E sweep in Gram-matrix form (BNMF_EGRAM=0: k_e_sweep), when P fits in shared memory
+  if (gram_buf && e_gram_smem(K, N) <= (size_t)200 * 1024 && !(getenv("BNMF_EGRAM") && atoi(getenv("BNMF_EGRAM")) == 0)) {
+    eg_smem = e_gram_smem(K, N);
+    CK(cudaFuncSetAttribute(k_e_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eg_smem));
+  }
   // Normal likelihood: Mhat on the tensor cores
   if (cfg.likelihood == BNMF_NORMAL && N <= TC_MAX_N && !(getenv("BNMF_TC") && atoi(getenv("BNMF_TC")) == 0)) {
     tc_smem = tc_smem_bytes<T>(N);
@@ -142,7 +147,7 @@ template <typename T> int Sampler<T>::p_gram_launch() {
   constexpr int PW = 4;
   k_p_gram<T, PW><<<(K + PW - 1) / PW, 32 * PW, (size_t)PW * N * (1 + 3 * P_PRE) * sizeof(double), stream>>>(d, gram_buf); mark("k_p_gram");
   launches += 3;
-  return mhat_rebuild();
+  return eg_smem ? 0 : mhat_rebuild();       // (the Gram-matrix E sweep reads no Mhat: it is rebuilt once, after that sweep)
 }
 
 template <typename T> int Sampler<T>::p_rows_launch() {
@@ -221,7 +226,10 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
         launches += 2;
       }
     }
-    {
+    if (gram_buf && eg_smem) {       // Normal likelihood: both sweeps through Gram matrices, Mhat from the tensor cores afterwards
+      k_e_gram<T><<<(unsigned)((G + EG_G - 1) / EG_G), EG_T, eg_smem, stream>>>(d); mark("k_e_gram"); ++launches;
+      if (mhat_rebuild()) return 1;
+    } else {
       const unsigned eg = (unsigned)((G + e_slots - 1) / e_slots);
       const int np = (pr_cs || gram_buf) ? -1 : N - 1;
       if (e_lpg == 8) k_e_sweep<T, 8><<<eg, 32 * e_wpb, e_smem, stream>>>(d, np, e_stage);

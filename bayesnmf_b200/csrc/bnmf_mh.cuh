@@ -865,6 +865,157 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
 }
 
 // ------------------------------------------------------------------------------
+// k_e_gram: the E sweep of the NORMAL likelihood in Gram-matrix form (get_mu_sigmasq_En_normal +
+// sample_En_normal, R/sample_En.R:131-184, :54-86).  With sigmasq[k,g] = sigmasq_g the sums over the
+// mutation types of the reference's conditional of E[n,g] collapse onto two small objects,
+//     num1 = ( (P' M)[n,g] - sum_{m != n} (P' P)[n,m] A_m E[m,g] ) / sigmasq_g ,  den = A_n (P' P)[n,n] / sigmasq_g
+// (E[m,g] the current value: already redrawn for m < n) -- the transpose of what k_p_gram does for P.
+// One thread per genome: its column of the data goes through shared memory once (coalesced), c = P' M[., g]
+// is accumulated eight signatures at a time in registers, then the N conditionals are a chain of N-term
+// dot products with P' P (shared memory, broadcast) and N truncated-normal draws.  Mhat is neither read nor
+// kept up to date: it is rebuilt once after the sweep (mhat_rebuild -> the tensor cores) for sigmasq and the
+// metrics.  Algebraically the reference's sums, not their summation order.
+// ------------------------------------------------------------------------------
+constexpr int EG_G = 32, EG_T = 4 * EG_G;         // genomes per block, four threads per genome
+__host__ __device__ inline size_t e_gram_smem(int K, int N) {
+  const int NPAD = (N + 7) & ~7;
+  return ((size_t)K * NPAD + (size_t)N * N + (size_t)EG_G * (K + 1) + (size_t)7 * N * EG_G) * sizeof(double) + 64 * sizeof(int);
+}
+template <typename T>
+__global__ void __launch_bounds__(EG_T) k_e_gram(Dev<T> d) {
+  extern __shared__ double egs[];
+  const int K = d.K, N = d.N, NPAD = (N + 7) & ~7;
+  double* Ps = egs;                                   // [K][NPAD]   P, zero padded
+  double* Q = Ps + (size_t)K * NPAD;                  // [N][N]      (P' P)[n,m] A_m
+  double* Ms = Q + (size_t)N * N;                     // [EG_G][K+1] the block's columns of the data
+  double* cs = Ms + (size_t)EG_G * (K + 1);           // [N][EG_G]   P' M[., g]
+  double* es = cs + (size_t)N * EG_G;                 // [N][EG_G]   E[., g], current
+  double* q1 = es + (size_t)N * EG_G;                 // [N][EG_G]   Lambda_e | Mu_e
+  double* q2 = q1 + (size_t)N * EG_G;                 // [N][EG_G]   Sigmasq_e
+  double* vZ = q2 + (size_t)N * EG_G;                 // [N][EG_G]   the variates of attempt 0 of every draw (tn_variates)
+  double* vE = vZ + (size_t)N * EG_G;
+  double* vU = vE + (size_t)N * EG_G;
+  int* nzs = reinterpret_cast<int*>(vU + (size_t)N * EG_G);   // [N] "row n of E got a non-zero"
+  const int t = threadIdx.x, gl = t >> 2, q = t & 3, lane_in_warp = t & 31;
+  const long long g0 = (long long)blockIdx.x * EG_G, g = g0 + gl;
+  const bool valid = g < d.G;
+  const int iter = d.ctrl->iter;
+  for (int i = t; i < K * NPAD; i += EG_T) { const int k = i / NPAD, n = i - k * NPAD; Ps[i] = n < N ? (double)d.P[k + (long long)K * n] : 0.0; }
+  {   // the block's EG_G columns of the data are one contiguous stretch of memory
+    const long long ng = d.G - g0 < EG_G ? d.G - g0 : EG_G;
+    const T* src = d.Mr + (long long)K * g0;
+    for (long long i = t; i < ng * K; i += EG_T) { const int c = (int)(i / K), k = (int)(i - (long long)c * K); Ms[(size_t)c * (K + 1) + k] = (double)src[i]; }
+  }
+  if (t < N) nzs[t] = 0;
+  // everything the chain reads besides the two Gram objects, in parallel: prior parameters, E, the variates
+  if (valid) for (int n = q; n < N; n += 4) {
+    const long long idx = n + (long long)N * g;
+    es[n * EG_G + gl] = (double)d.E[idx];
+    if (d.prior == PRIOR_EXPONENTIAL) { q1[n * EG_G + gl] = (double)d.Lambda_e[idx]; q2[n * EG_G + gl] = 0.0; }
+    else { q1[n * EG_G + gl] = (double)d.Mu_e[idx]; q2[n * EG_G + gl] = (double)d.Sigmasq_e[idx]; }
+    tn_variates(make_stream(d.seed, iter, PUR_E, n + (long long)N * (d.g0 + g)), 0, vZ[n * EG_G + gl], vE[n * EG_G + gl], vU[n * EG_G + gl]);
+  }
+  __syncthreads();
+  for (int i = t; i < N * N; i += EG_T) {
+    const int a = i / N, b = i - a * N;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += Ps[k * NPAD + a] * Ps[k * NPAD + b];
+    Q[i] = (a == b || d.A[b]) ? s : 0.0;              // the diagonal is den; off the diagonal excluded signatures drop out
+  }
+  if (valid) {
+    const double* mcol = Ms + (size_t)gl * (K + 1);
+    for (int n0 = 8 * q; n0 < N; n0 += 32) {          // eight signatures at a time in registers
+      double acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const double m = mcol[k];
+        const double* pr = Ps + k * NPAD + n0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += pr[j] * m;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (n0 + j < N) cs[(n0 + j) * EG_G + gl] = acc[j];
+    }
+  }
+  __syncthreads();
+  const unsigned gmask = __ballot_sync(0xffffffffu, valid);     // (the four lanes of a genome are valid together)
+  if (valid) {
+    const double inv_sg = 1.0 / (double)d.sigmasq[g];
+    for (int n = 0; n < N; ++n) {
+      const int An = d.A[n];
+      const long long idx = n + (long long)N * g;
+      const Stream st = make_stream(d.seed, iter, PUR_E, n + (long long)N * (d.g0 + g));
+      double x;
+      if (An == 0 || d.nzP[n] == 0) {                               // R/sample_En.R:12,56
+        x = prior_draw(d, st, 1, idx);
+      } else {
+        const double* qr = Q + n * N;
+        double dot = 0.0;
+        for (int m = q; m < N; m += 4) if (m != n) dot += qr[m] * es[m * EG_G + gl];
+        dot += __shfl_xor_sync(gmask, dot, 1);
+        dot += __shfl_xor_sync(gmask, dot, 2);
+        const double num1 = (cs[n * EG_G + gl] - dot) * inv_sg;
+        double den = qr[n] * inv_sg;
+        double mu, v;
+        if (d.prior == PRIOR_EXPONENTIAL) {
+          mu = (num1 - q1[n * EG_G + gl]) / den; v = 1.0 / den;
+        } else {
+          const double s2 = q2[n * EG_G + gl];
+          den = den + 1.0 / s2;
+          mu = (num1 + q1[n * EG_G + gl] / s2) / den; v = 1.0 / den;
+        }
+        // attempt 0 of truncnorm0_draw from the variates staged above; later attempts (rare) in place
+        const double sd = sqrt(v), alpha = -mu / sd;
+        bool found = false;
+        if (alpha <= 0.45) {
+          const double zz = vZ[n * EG_G + gl];
+          if (zz >= alpha) { x = mu + sd * zz; x = x < 0.0 ? 0.0 : x; found = true; }
+        } else {
+          const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
+          const double ee = vE[n * EG_G + gl] / lam;
+          const double dz = (alpha + ee) - lam;
+          if (vU[n * EG_G + gl] <= -0.5 * (dz * dz)) { x = sd * ee; found = true; }
+        }
+        // attempts 1, 2, ...: the four lanes of a genome try four attempts at a time, the first accepted one counts
+        // (same attempts, same order, same expressions as truncnorm0_draw).  This branch is uniform over the warp's
+        // valid lanes (A_n and nzP[n] are), and the loop runs until no genome of the warp needs another round: every
+        // lane of `gmask` executes every ballot / shuffle.
+        {
+          bool need = !found;
+          const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
+          const int grp = lane_in_warp & ~3;
+          for (uint32_t t0 = 1; __any_sync(gmask, need) && t0 < 4096u; t0 += 4) {
+            bool ok = false; double xc = 0.0;
+            if (need) {
+              double z, e, u;
+              tn_variates(st, (int)(t0 + q), z, e, u);
+              if (alpha <= 0.45) { ok = z >= alpha; xc = mu + sd * z; xc = xc < 0.0 ? 0.0 : xc; }
+              else { const double ee = e / lam; const double dz = (alpha + ee) - lam; ok = u <= -0.5 * (dz * dz); xc = sd * ee; }
+            }
+            const unsigned bits = (__ballot_sync(gmask, ok) >> grp) & 0xFu;
+            const int first = bits ? __ffs((int)bits) - 1 : 0;
+            xc = __shfl_sync(gmask, xc, grp + first);
+            if (need && bits) { x = xc; need = false; found = true; }
+          }
+          if (!found) x = alpha <= 0.45 ? fmax(mu + sd * alpha, 0.0) : 0.0;       // (truncnorm0_draw's value when every attempt fails)
+        }
+      }
+      x = (double)(T)x;
+      __syncwarp(gmask);                     // every lane of the genome has read es[n] of the step before
+      if (q == 0) {
+        es[n * EG_G + gl] = x;
+        d.E[idx] = (T)x;
+        if (x != 0.0) nzs[n] = 1;
+      }
+      __syncwarp(gmask);
+    }
+  }
+  __syncthreads();
+  if (t < N && nzs[t]) atomicOr(&d.nzE[(iter & 1) * N + t], 1);
+}
+
+// ------------------------------------------------------------------------------
 // Rank learning (R/sample_params.R:101-241).
 // k_r: R | A  ~ categorical over 0..N with weight (q_r^{sum A} (1 - q_r)^{N - sum A})^T.
 // ------------------------------------------------------------------------------
