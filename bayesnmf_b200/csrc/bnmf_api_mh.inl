@@ -67,9 +67,17 @@ template <typename T> int Sampler<T>::mh_setup() {
     if (dalloc(&gram_part, (long long)gram_chunks * len) || dalloc(&gram_buf, len)) return 1;
   }
   // Normal likelihood: the E sweep in Gram-matrix form (BNMF_EGRAM=0: k_e_sweep), when P fits in shared memory
-  if (gram_buf && e_gram_smem(K, N) <= (size_t)200 * 1024 && !(getenv("BNMF_EGRAM") && atoi(getenv("BNMF_EGRAM")) == 0)) {
-    eg_smem = e_gram_smem(K, N);
-    CK(cudaFuncSetAttribute(k_e_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eg_smem));
+  if (gram_buf && !(getenv("BNMF_EGRAM") && atoi(getenv("BNMF_EGRAM")) == 0)) {
+    // genomes per block: the whole shard in one wave of two blocks per SM when that fits the shared memory (a
+    // genome's chain of N conditionals is latency; a second wave doubles it), else the most that fits
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    int gb = (int)((G + 2LL * sms - 1) / (2LL * sms));
+    gb = std::max(32, std::min(96, (gb + 3) & ~3));
+    while (gb > 32 && e_gram_smem(K, N, gb) > (size_t)110 * 1024) gb -= 4;
+    if (e_gram_smem(K, N, gb) <= (size_t)110 * 1024) {
+      eg_gb = gb; eg_smem = e_gram_smem(K, N, gb);
+      CK(cudaFuncSetAttribute(k_e_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eg_smem));
+    }
   }
   // Normal likelihood: Mhat on the tensor cores
   if (cfg.likelihood == BNMF_NORMAL && N <= TC_MAX_N && !(getenv("BNMF_TC") && atoi(getenv("BNMF_TC")) == 0)) {
@@ -227,7 +235,7 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
       }
     }
     if (gram_buf && eg_smem) {       // Normal likelihood: both sweeps through Gram matrices, Mhat from the tensor cores afterwards
-      k_e_gram<T><<<(unsigned)((G + EG_G - 1) / EG_G), EG_T, eg_smem, stream>>>(d); mark("k_e_gram"); ++launches;
+      k_e_gram<T><<<(unsigned)((G + eg_gb - 1) / eg_gb), EG_T, eg_smem, stream>>>(d, eg_gb); mark("k_e_gram"); ++launches;
       if (mhat_rebuild()) return 1;
     } else {
       const unsigned eg = (unsigned)((G + e_slots - 1) / e_slots);

@@ -876,44 +876,51 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
 // kept up to date: it is rebuilt once after the sweep (mhat_rebuild -> the tensor cores) for sigmasq and the
 // metrics.  Algebraically the reference's sums, not their summation order.
 // ------------------------------------------------------------------------------
-constexpr int EG_G = 32, EG_T = 4 * EG_G;         // genomes per block, four threads per genome
-__host__ __device__ inline size_t e_gram_smem(int K, int N) {
+constexpr int EG_T = 128, EG_KC = 16, EG_PRE = 2;    // threads per block, rows of the data staged at a time, staged attempts per draw
+constexpr int EG_ARR = 4 + 3 * EG_PRE;               // per-genome arrays of N doubles: c, E, two prior parameters, the variates
+__host__ __device__ inline size_t e_gram_smem(int K, int N, int GB) {
   const int NPAD = (N + 7) & ~7;
-  return ((size_t)K * NPAD + (size_t)N * N + (size_t)EG_G * (K + 1) + (size_t)7 * N * EG_G) * sizeof(double) + 64 * sizeof(int);
+  return ((size_t)K * NPAD + (size_t)N * N + (size_t)GB * (EG_KC + 1) + (size_t)EG_ARR * N * GB) * sizeof(double) + 64 * sizeof(int);
 }
+// Work layout: 128 threads per GB genomes (GB <= 96, chosen by the host so that the whole shard is resident in one
+// wave of two blocks per SM when it fits).  The parallel phases use every thread (staging, P' P, the variates of the
+// first EG_PRE attempts of every draw, P' M: thread (genome, half) accumulates eight signatures at a time in
+// registers while the block streams the data through shared memory 16 mutation types at a time); the chain of the
+// N conditionals is scalar work per genome and runs one thread per genome, with the later attempts of a rejected
+// draw (rare after two staged ones) tried warp-uniformly.
 template <typename T>
-__global__ void __launch_bounds__(EG_T) k_e_gram(Dev<T> d) {
+__global__ void __launch_bounds__(EG_T) k_e_gram(Dev<T> d, int GB) {
   extern __shared__ double egs[];
   const int K = d.K, N = d.N, NPAD = (N + 7) & ~7;
   double* Ps = egs;                                   // [K][NPAD]   P, zero padded
   double* Q = Ps + (size_t)K * NPAD;                  // [N][N]      (P' P)[n,m] A_m
-  double* Ms = Q + (size_t)N * N;                     // [EG_G][K+1] the block's columns of the data
-  double* cs = Ms + (size_t)EG_G * (K + 1);           // [N][EG_G]   P' M[., g]
-  double* es = cs + (size_t)N * EG_G;                 // [N][EG_G]   E[., g], current
-  double* q1 = es + (size_t)N * EG_G;                 // [N][EG_G]   Lambda_e | Mu_e
-  double* q2 = q1 + (size_t)N * EG_G;                 // [N][EG_G]   Sigmasq_e
-  double* vZ = q2 + (size_t)N * EG_G;                 // [N][EG_G]   the variates of attempt 0 of every draw (tn_variates)
-  double* vE = vZ + (size_t)N * EG_G;
-  double* vU = vE + (size_t)N * EG_G;
-  int* nzs = reinterpret_cast<int*>(vU + (size_t)N * EG_G);   // [N] "row n of E got a non-zero"
-  const int t = threadIdx.x, gl = t >> 2, q = t & 3, lane_in_warp = t & 31;
-  const long long g0 = (long long)blockIdx.x * EG_G, g = g0 + gl;
-  const bool valid = g < d.G;
+  double* Ms = Q + (size_t)N * N;                     // [GB][EG_KC+1] rows kc .. kc+15 of the block's columns of the data
+  double* cs = Ms + (size_t)GB * (EG_KC + 1);         // [N][GB]     P' M[., g]
+  double* es = cs + (size_t)N * GB;                   // [N][GB]     E[., g], current
+  double* q1 = es + (size_t)N * GB;                   // [N][GB]     Lambda_e | Mu_e
+  double* q2 = q1 + (size_t)N * GB;                   // [N][GB]     Sigmasq_e
+  double* vZ = q2 + (size_t)N * GB;                   // [EG_PRE][N][GB]  the variates of the first attempts of every draw (tn_variates)
+  double* vE = vZ + (size_t)EG_PRE * N * GB;
+  double* vU = vE + (size_t)EG_PRE * N * GB;
+  int* nzs = reinterpret_cast<int*>(vU + (size_t)EG_PRE * N * GB);   // [N] "row n of E got a non-zero"
+  const int t = threadIdx.x;
+  const long long g0 = (long long)blockIdx.x * GB;
+  const int ng = (int)(d.G - g0 < GB ? d.G - g0 : GB);
   const int iter = d.ctrl->iter;
   for (int i = t; i < K * NPAD; i += EG_T) { const int k = i / NPAD, n = i - k * NPAD; Ps[i] = n < N ? (double)d.P[k + (long long)K * n] : 0.0; }
-  {   // the block's EG_G columns of the data are one contiguous stretch of memory
-    const long long ng = d.G - g0 < EG_G ? d.G - g0 : EG_G;
-    const T* src = d.Mr + (long long)K * g0;
-    for (long long i = t; i < ng * K; i += EG_T) { const int c = (int)(i / K), k = (int)(i - (long long)c * K); Ms[(size_t)c * (K + 1) + k] = (double)src[i]; }
-  }
   if (t < N) nzs[t] = 0;
   // everything the chain reads besides the two Gram objects, in parallel: prior parameters, E, the variates
-  if (valid) for (int n = q; n < N; n += 4) {
-    const long long idx = n + (long long)N * g;
-    es[n * EG_G + gl] = (double)d.E[idx];
-    if (d.prior == PRIOR_EXPONENTIAL) { q1[n * EG_G + gl] = (double)d.Lambda_e[idx]; q2[n * EG_G + gl] = 0.0; }
-    else { q1[n * EG_G + gl] = (double)d.Mu_e[idx]; q2[n * EG_G + gl] = (double)d.Sigmasq_e[idx]; }
-    tn_variates(make_stream(d.seed, iter, PUR_E, n + (long long)N * (d.g0 + g)), 0, vZ[n * EG_G + gl], vE[n * EG_G + gl], vU[n * EG_G + gl]);
+  for (int i = t; i < N * ng; i += EG_T) {            // i = n + N * genome: E and the prior parameters are read coalesced
+    const int gl = i / N, n = i - gl * N;
+    const long long idx = (long long)N * g0 + i;
+    es[n * GB + gl] = (double)d.E[idx];
+    if (d.prior == PRIOR_EXPONENTIAL) { q1[n * GB + gl] = (double)d.Lambda_e[idx]; q2[n * GB + gl] = 0.0; }
+    else { q1[n * GB + gl] = (double)d.Mu_e[idx]; q2[n * GB + gl] = (double)d.Sigmasq_e[idx]; }
+  }
+  for (int i = t; i < EG_PRE * N * ng; i += EG_T) {
+    const int a = i / (N * ng), r = i - a * (N * ng), gl = r / N, n = r - gl * N;
+    const size_t o = ((size_t)a * N + n) * GB + gl;
+    tn_variates(make_stream(d.seed, iter, PUR_E, (long long)N * (d.g0 + g0) + r), a, vZ[o], vE[o], vU[o]);
   }
   __syncthreads();
   for (int i = t; i < N * N; i += EG_T) {
@@ -922,93 +929,112 @@ __global__ void __launch_bounds__(EG_T) k_e_gram(Dev<T> d) {
     for (int k = 0; k < K; ++k) s += Ps[k * NPAD + a] * Ps[k * NPAD + b];
     Q[i] = (a == b || d.A[b]) ? s : 0.0;              // the diagonal is den; off the diagonal excluded signatures drop out
   }
-  if (valid) {
-    const double* mcol = Ms + (size_t)gl * (K + 1);
-    for (int n0 = 8 * q; n0 < N; n0 += 32) {          // eight signatures at a time in registers
-      double acc[8];
+  // c = P' M[., g]: thread u takes genome u mod GB... two "halves" of threads split the signature groups of 8
+  {
+    const int HT = EG_T / 2;                          // 64 threads per half; a half covers the genomes in rounds of 64
+    const int h = t / HT, tl = t - h * HT;
+    const T* src = d.Mr + (long long)K * g0;
+    const int NG8 = NPAD / 8;
+    const int rounds = (NG8 + 1) / 2;                 // both halves run the same number of rounds (an odd group count: the second half idles in the last)
+    for (int r = 0; r < rounds; ++r) {
+      const int n0 = 8 * (2 * r + h);
+      const bool live = n0 < NPAD;
+      for (int gb = 0; gb < GB; gb += HT) {           // genomes gb + tl
+        const int gl = gb + tl;
+        double acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.0;
-      for (int k = 0; k < K; ++k) {
-        const double m = mcol[k];
-        const double* pr = Ps + k * NPAD + n0;
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+        for (int kc = 0; kc < K; kc += EG_KC) {
+          __syncthreads();                            // (the chunk before has been consumed)
+          const int rows = K - kc < EG_KC ? K - kc : EG_KC;
+          for (int i = t; i < ng * EG_KC; i += EG_T) {  // 16 consecutive doubles of a column = one 128-byte line
+            const int c = i / EG_KC, j = i - c * EG_KC;
+            Ms[c * (EG_KC + 1) + j] = j < rows ? (double)src[(long long)c * K + kc + j] : 0.0;
+          }
+          __syncthreads();
+          if (live && gl < ng) {
+            const double* mrow = Ms + gl * (EG_KC + 1);
+            for (int j = 0; j < rows; ++j) {
+              const double m = mrow[j];
+              const double* pr = Ps + (kc + j) * NPAD + n0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += pr[j] * m;
+              for (int u = 0; u < 8; ++u) acc[u] += pr[u] * m;
+            }
+          }
+        }
+        if (live && gl < ng) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (n0 + j < N) cs[(n0 + j) * GB + gl] = acc[j];
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (n0 + j < N) cs[(n0 + j) * EG_G + gl] = acc[j];
     }
   }
   __syncthreads();
-  const unsigned gmask = __ballot_sync(0xffffffffu, valid);     // (the four lanes of a genome are valid together)
-  if (valid) {
-    const double inv_sg = 1.0 / (double)d.sigmasq[g];
-    for (int n = 0; n < N; ++n) {
-      const int An = d.A[n];
-      const long long idx = n + (long long)N * g;
-      const Stream st = make_stream(d.seed, iter, PUR_E, n + (long long)N * (d.g0 + g));
-      double x;
-      if (An == 0 || d.nzP[n] == 0) {                               // R/sample_En.R:12,56
-        x = prior_draw(d, st, 1, idx);
-      } else {
-        const double* qr = Q + n * N;
-        double dot = 0.0;
-        for (int m = q; m < N; m += 4) if (m != n) dot += qr[m] * es[m * EG_G + gl];
-        dot += __shfl_xor_sync(gmask, dot, 1);
-        dot += __shfl_xor_sync(gmask, dot, 2);
-        const double num1 = (cs[n * EG_G + gl] - dot) * inv_sg;
-        double den = qr[n] * inv_sg;
-        double mu, v;
-        if (d.prior == PRIOR_EXPONENTIAL) {
-          mu = (num1 - q1[n * EG_G + gl]) / den; v = 1.0 / den;
+  // ---- the chain: one thread per genome (GB <= 96 < 128 threads) ----
+  {
+    const int gl = t;
+    const bool valid = gl < ng;
+    const unsigned gmask = __ballot_sync(0xffffffffu, valid);
+    const long long g = g0 + gl;
+    if (valid) {
+      const double inv_sg = 1.0 / (double)d.sigmasq[g];
+      for (int n = 0; n < N; ++n) {
+        const int An = d.A[n];
+        const long long idx = n + (long long)N * g;
+        const Stream st = make_stream(d.seed, iter, PUR_E, n + (long long)N * (d.g0 + g));
+        double x;
+        if (An == 0 || d.nzP[n] == 0) {                               // R/sample_En.R:12,56
+          x = prior_draw(d, st, 1, idx);
         } else {
-          const double s2 = q2[n * EG_G + gl];
-          den = den + 1.0 / s2;
-          mu = (num1 + q1[n * EG_G + gl] / s2) / den; v = 1.0 / den;
-        }
-        // attempt 0 of truncnorm0_draw from the variates staged above; later attempts (rare) in place
-        const double sd = sqrt(v), alpha = -mu / sd;
-        bool found = false;
-        if (alpha <= 0.45) {
-          const double zz = vZ[n * EG_G + gl];
-          if (zz >= alpha) { x = mu + sd * zz; x = x < 0.0 ? 0.0 : x; found = true; }
-        } else {
+          const double* qr = Q + n * N;
+          double dot0 = 0.0, dot1 = 0.0;
+          int m = 0;
+          for (; m + 1 < N; m += 2) {
+            if (m != n) dot0 += qr[m] * es[m * GB + gl];
+            if (m + 1 != n) dot1 += qr[m + 1] * es[(m + 1) * GB + gl];
+          }
+          if (m < N && m != n) dot0 += qr[m] * es[m * GB + gl];
+          const double num1 = (cs[n * GB + gl] - (dot0 + dot1)) * inv_sg;
+          double den = qr[n] * inv_sg;
+          double mu, v;
+          if (d.prior == PRIOR_EXPONENTIAL) {
+            mu = (num1 - q1[n * GB + gl]) / den; v = 1.0 / den;
+          } else {
+            const double s2 = q2[n * GB + gl];
+            den = den + 1.0 / s2;
+            mu = (num1 + q1[n * GB + gl] / s2) / den; v = 1.0 / den;
+          }
+          // the first EG_PRE attempts of truncnorm0_draw from the variates staged above
+          const double sd = sqrt(v), alpha = -mu / sd;
           const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
-          const double ee = vE[n * EG_G + gl] / lam;
-          const double dz = (alpha + ee) - lam;
-          if (vU[n * EG_G + gl] <= -0.5 * (dz * dz)) { x = sd * ee; found = true; }
-        }
-        // attempts 1, 2, ...: the four lanes of a genome try four attempts at a time, the first accepted one counts
-        // (same attempts, same order, same expressions as truncnorm0_draw).  This branch is uniform over the warp's
-        // valid lanes (A_n and nzP[n] are), and the loop runs until no genome of the warp needs another round: every
-        // lane of `gmask` executes every ballot / shuffle.
-        {
-          bool need = !found;
-          const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
-          const int grp = lane_in_warp & ~3;
-          for (uint32_t t0 = 1; __any_sync(gmask, need) && t0 < 4096u; t0 += 4) {
-            bool ok = false; double xc = 0.0;
-            if (need) {
-              double z, e, u;
-              tn_variates(st, (int)(t0 + q), z, e, u);
-              if (alpha <= 0.45) { ok = z >= alpha; xc = mu + sd * z; xc = xc < 0.0 ? 0.0 : xc; }
-              else { const double ee = e / lam; const double dz = (alpha + ee) - lam; ok = u <= -0.5 * (dz * dz); xc = sd * ee; }
+          bool found = false;
+          x = 0.0;
+#pragma unroll
+          for (int a = 0; a < EG_PRE; ++a) {
+            const size_t o = ((size_t)a * N + n) * GB + gl;
+            if (!found) {
+              if (alpha <= 0.45) { const double zz = vZ[o]; if (zz >= alpha) { x = mu + sd * zz; x = x < 0.0 ? 0.0 : x; found = true; } }
+              else { const double ee = vE[o] / lam; const double dz = (alpha + ee) - lam; if (vU[o] <= -0.5 * (dz * dz)) { x = sd * ee; found = true; } }
             }
-            const unsigned bits = (__ballot_sync(gmask, ok) >> grp) & 0xFu;
-            const int first = bits ? __ffs((int)bits) - 1 : 0;
-            xc = __shfl_sync(gmask, xc, grp + first);
-            if (need && bits) { x = xc; need = false; found = true; }
+          }
+          // later attempts (same attempts, same order, same expressions as truncnorm0_draw).  This branch is uniform
+          // over the warp's valid lanes (A_n and nzP[n] are); the loop runs until no genome of the warp needs another
+          // attempt, so that the rejected lanes share their passes through the variate code
+          for (uint32_t at = EG_PRE; __any_sync(gmask, !found) && at < 4096u; ++at) {
+            if (!found) {
+              double z, e, u;
+              tn_variates(st, (int)at, z, e, u);
+              if (alpha <= 0.45) { if (z >= alpha) { x = mu + sd * z; x = x < 0.0 ? 0.0 : x; found = true; } }
+              else { const double ee = e / lam; const double dz = (alpha + ee) - lam; if (u <= -0.5 * (dz * dz)) { x = sd * ee; found = true; } }
+            }
           }
           if (!found) x = alpha <= 0.45 ? fmax(mu + sd * alpha, 0.0) : 0.0;       // (truncnorm0_draw's value when every attempt fails)
         }
-      }
-      x = (double)(T)x;
-      __syncwarp(gmask);                     // every lane of the genome has read es[n] of the step before
-      if (q == 0) {
-        es[n * EG_G + gl] = x;
+        x = (double)(T)x;
+        es[n * GB + gl] = x;
         d.E[idx] = (T)x;
         if (x != 0.0) nzs[n] = 1;
       }
-      __syncwarp(gmask);
     }
   }
   __syncthreads();
