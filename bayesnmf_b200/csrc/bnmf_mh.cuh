@@ -876,13 +876,13 @@ __global__ void k_e_sweep(Dev<T> d, int n_prev, int stage) {
 // kept up to date: it is rebuilt once after the sweep (mhat_rebuild -> the tensor cores) for sigmasq and the
 // metrics.  Algebraically the reference's sums, not their summation order.
 // ------------------------------------------------------------------------------
-constexpr int EG_T = 128, EG_KC = 16, EG_PRE = 2;    // threads per block, rows of the data staged at a time, staged attempts per draw
+constexpr int EG_T = 192, EG_KC = 16, EG_PRE = 2;    // threads per block, rows of the data staged at a time, staged attempts per draw
 constexpr int EG_ARR = 4 + 3 * EG_PRE;               // per-genome arrays of N doubles: c, E, two prior parameters, the variates
 __host__ __device__ inline size_t e_gram_smem(int K, int N, int GB) {
   const int NPAD = (N + 7) & ~7;
   return ((size_t)K * NPAD + (size_t)N * N + (size_t)GB * (EG_KC + 1) + (size_t)EG_ARR * N * GB) * sizeof(double) + 64 * sizeof(int);
 }
-// Work layout: 128 threads per GB genomes (GB <= 96, chosen by the host so that the whole shard is resident in one
+// Work layout: 192 threads per GB genomes (GB <= 96, chosen by the host so that the whole shard is resident in one
 // wave of two blocks per SM when it fits).  The parallel phases use every thread (staging, P' P, the variates of the
 // first EG_PRE attempts of every draw, P' M: thread (genome, half) accumulates eight signatures at a time in
 // registers while the block streams the data through shared memory 16 mutation types at a time); the chain of the
@@ -914,8 +914,10 @@ __global__ void __launch_bounds__(EG_T) k_e_gram(Dev<T> d, int GB) {
     const int gl = i / N, n = i - gl * N;
     const long long idx = (long long)N * g0 + i;
     es[n * GB + gl] = (double)d.E[idx];
-    if (d.prior == PRIOR_EXPONENTIAL) { q1[n * GB + gl] = (double)d.Lambda_e[idx]; q2[n * GB + gl] = 0.0; }
-    else { q1[n * GB + gl] = (double)d.Mu_e[idx]; q2[n * GB + gl] = (double)d.Sigmasq_e[idx]; }
+    // the prior's two contributions to the conditional, with their divisions done here, outside the chain:
+    //   q1 = what is added to num1 (-Lambda | Mu / Sigmasq),  q2 = what is added to den (0 | 1 / Sigmasq)
+    if (d.prior == PRIOR_EXPONENTIAL) { q1[n * GB + gl] = -(double)d.Lambda_e[idx]; q2[n * GB + gl] = 0.0; }
+    else { const double s2 = (double)d.Sigmasq_e[idx]; q1[n * GB + gl] = (double)d.Mu_e[idx] / s2; q2[n * GB + gl] = 1.0 / s2; }
   }
   for (int i = t; i < EG_PRE * N * ng; i += EG_T) {
     const int a = i / (N * ng), r = i - a * (N * ng), gl = r / N, n = r - gl * N;
@@ -931,7 +933,7 @@ __global__ void __launch_bounds__(EG_T) k_e_gram(Dev<T> d, int GB) {
   }
   // c = P' M[., g]: thread u takes genome u mod GB... two "halves" of threads split the signature groups of 8
   {
-    const int HT = EG_T / 2;                          // 64 threads per half; a half covers the genomes in rounds of 64
+    const int HT = EG_T / 2;                          // 96 threads per half >= GB: a half covers the genomes in one pass
     const int h = t / HT, tl = t - h * HT;
     const T* src = d.Mr + (long long)K * g0;
     const int NG8 = NPAD / 8;
@@ -994,19 +996,14 @@ __global__ void __launch_bounds__(EG_T) k_e_gram(Dev<T> d, int GB) {
             if (m + 1 != n) dot1 += qr[m + 1] * es[(m + 1) * GB + gl];
           }
           if (m < N && m != n) dot0 += qr[m] * es[m * GB + gl];
-          const double num1 = (cs[n * GB + gl] - (dot0 + dot1)) * inv_sg;
-          double den = qr[n] * inv_sg;
-          double mu, v;
-          if (d.prior == PRIOR_EXPONENTIAL) {
-            mu = (num1 - q1[n * GB + gl]) / den; v = 1.0 / den;
-          } else {
-            const double s2 = q2[n * GB + gl];
-            den = den + 1.0 / s2;
-            mu = (num1 + q1[n * GB + gl] / s2) / den; v = 1.0 / den;
-          }
-          // the first EG_PRE attempts of truncnorm0_draw from the variates staged above
-          const double sd = sqrt(v), alpha = -mu / sd;
-          const double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
+          // mu = (num1 + q1) / den, v = 1 / den (R/sample_En.R:150-184) with one division and one square root on the
+          // chain: sd = sqrt(v), mu = (num1 + q1) v, alpha = -mu / sd = -(num1 + q1) sd
+          const double num = (cs[n * GB + gl] - (dot0 + dot1)) * inv_sg + q1[n * GB + gl];
+          const double den = qr[n] * inv_sg + q2[n * GB + gl];
+          const double v = 1.0 / den;
+          const double mu = num * v;
+          const double sd = sqrt(v), alpha = -(num * sd);
+          const double lam = alpha > 0.45 ? 0.5 * (alpha + sqrt(alpha * alpha + 4.0)) : 1.0;
           bool found = false;
           x = 0.0;
 #pragma unroll
