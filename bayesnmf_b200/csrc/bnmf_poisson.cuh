@@ -550,13 +550,14 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
   const long long nA = (long long)rtsA * ctA;
   const long long n_items = nA + (long long)rtsB * (cts - ctA);
   {
-    int next = 0;
-    if (lane == 0) next = atomicAdd(work_ctr, 1);
-    next = __shfl_sync(0xffffffffu, next, 0);
+    // the first item of a warp is its own number (no 2,368 tickets drawn from one counter at once); later ones
+    // come from the queue, which starts behind them
+    const int n_warps = (int)gridDim.x * ZWarps<NP>::value;
+    int next = (int)blockIdx.x * ZWarps<NP>::value + wid;
   for (;;) {
     const int item = next;
     if (item >= n_items) break;
-    if (lane == 0) next = atomicAdd(work_ctr, 1);      // the next ticket travels while this item is processed
+    if (lane == 0) next = n_warps + atomicAdd(work_ctr, 1);      // the next ticket travels while this item is processed
     // items in chunk-major order: chunk 0 (it holds the heaviest mutation types) of every column tile first, the
     // lightest chunk last -- longest processing time first, the warps that finish last are on the cheapest items
     // (a single row of the heaviest type over 32 genomes is ~8 rows' worth of picks: taken late it IS the tail)
