@@ -624,8 +624,34 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
           thr[n * 32 + lane] = n < N - 1 ? pick_thr(mul_rn<T>(acc, scale)) : 0xffffffffu;
         }
       }
-      // quads of this lane's cell and their offsets in the row's flattened quad list
+      // quads of this lane's cell
       const int q = work ? (int)(((unsigned)m + 3u) >> 2) : 0;
+      // Sparse rows (exome-like counts: a quad or two per cell): sharing out the row's quads costs more -- scan,
+      // cell table, spilled-cell fix-up: ~300 instructions -- than the idle lanes it saves.  Every lane then draws
+      // the picks of its own cell: its own threshold column, its own histogram column, nothing to fix up.
+      const int maxq = __reduce_max_sync(0xffffffffu, q);
+      if (32 * maxq <= __reduce_add_sync(0xffffffffu, q) + 80) {
+        if (q > 0) {
+          const unsigned long long cell = cell0 + (unsigned long long)k_this + (unsigned long long)((unsigned)K * (unsigned)lane);
+          const uint32_t col = thr_sa + 4u * (unsigned)lane;
+          ZPivots pv;
+          pv.mid = lds_u32_off<(NPAD / 2 - 1) * 128>(col);
+          pv.lo = lds_u32_off<(NPAD / 4 - 1) * 128>(col); pv.hi = lds_u32_off<(3 * NPAD / 4 - 1) * 128>(col);
+          pv.q0 = pv.q1 = pv.q2 = pv.q3 = 0xffffffffu;
+          if (NPAD >= 8) {
+            pv.q0 = lds_u32_off<(NPAD / 8 - 1) * 128>(col);
+            pv.q1 = lds_u32_off<(3 * NPAD / 8 - 1) * 128>(col);
+            pv.q2 = (5 * NPAD / 8 - 1 < TR) ? lds_u32_off<(5 * NPAD / 8 - 1) * 128>(col) : 0xffffffffu;
+            pv.q3 = (7 * NPAD / 8 - 1 < TR) ? lds_u32_off<(7 * NPAD / 8 - 1) * 128>(col) : 0xffffffffu;
+          }
+          for (int sub = 0; sub < q; ++sub) {
+            const U4 w = philox_rk((uint32_t)cell, (uint32_t)(cell >> 32), (uint32_t)sub, c3, rk);
+            zstat_quad<NPAD, false>(w, col, pv, m - 4 * sub, 4u * TR * 32);
+          }
+        }
+        __syncwarp();
+      } else {
+      // ---- dense rows: the quads of the 32 cells laid end to end, an equal share per lane ----
       int incl = q;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -714,6 +740,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
           __syncwarp();
         }
       }
+      }   // (dense rows)
       // the histogram keeps counting through the rows of the item (its columns are SE); the sum of
       // a row of it over the tile's cells, minus the same sum one row earlier, is this row's SP
       int mytot0 = 0, mytot1 = 0;
