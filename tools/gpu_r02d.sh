@@ -1,0 +1,23 @@
+#!/bin/bash
+# round 2, final 1-GPU call: whole GPU suite, smoke, every workload, reference arm, ncu launch list + full captures
+mkdir -p gpurun_out
+TAG=r02d
+timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/pytest_gpu_$TAG.log; tail -3 gpurun_out/pytest_gpu_$TAG.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke_$TAG.log
+for W in c3 c3-exome c1 c2 c4 c5; do
+  timeout 300 python bench.py --workload $W --steps 50 --warmup 5 2> gpurun_out/bench_${W}_$TAG.err > gpurun_out/bench_${W}_$TAG.json
+  python -c "
+import json; j=json.load(open('gpurun_out/bench_${W}_$TAG.json')); print('$W', round(j['value'],1), 'it/s e2e', round(j['e2e']['value'],1), 'roof', j['roofline']['kernel'], j['roofline']['frac'], 'cpu', round(j['cpu_baseline']['value'],3), j.get('mh_phase',{}).get('value'))"
+done
+timeout 300 python bench.py --workload c3 --precision f32 --steps 50 --warmup 5 --no-cpu-baseline 2> gpurun_out/bench_c3_f32_$TAG.err > gpurun_out/bench_c3_f32_$TAG.json
+python -c "
+import json; j=json.load(open('gpurun_out/bench_c3_f32_$TAG.json')); print('c3 f32', round(j['value'],1), 'it/s e2e', round(j['e2e']['value'],1))"
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2> gpurun_out/bench_ref_$TAG.err > gpurun_out/bench_ref_$TAG.json; cat gpurun_out/bench_ref_$TAG.json | cut -c1-400
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+timeout 200 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
+timeout 200 python tools/prof_z.py 4000 100000 > gpurun_out/plain_z_$TAG.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_zstat -s 3 -c 1 -f -o gpurun_out/prof_zstat_$TAG python tools/prof_z.py 4000 100000 > gpurun_out/ncu_z_$TAG.log 2>&1
+BNMF_GRAPH=0 timeout 200 python tools/prof_c5.py c4 > gpurun_out/plain_c4_$TAG.log 2>&1 &&
+BNMF_GRAPH=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_mhat_tc|k_e_gram" -s 2 -c 2 -f -o gpurun_out/prof_c4_$TAG python tools/prof_c5.py c4 > gpurun_out/ncu_c4_$TAG.log 2>&1
+tail -2 gpurun_out/ncu_c4_$TAG.log
