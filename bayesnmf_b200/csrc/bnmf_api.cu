@@ -276,7 +276,7 @@ struct Sampler : bnmf_handle {
   std::map<std::string, Hyper<T>*> hy;
   std::map<std::string, long long> hy_len;
   double* stage = nullptr; long long stage_len = 0;      // device double staging
-  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96; int ZR = 32, ZR_B = 2, z_ctB = 0;
+  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96; int ZR = 32, ZR_B = 2, z_ctB = 0; bool z_sparse = false;
   double* red_slices = nullptr; unsigned* red_ticket = nullptr;
   int* nanflags = nullptr;
   T* P_hist = nullptr; int32_t* A_hist = nullptr;
@@ -587,6 +587,9 @@ struct Sampler : bnmf_handle {
       d.ll_const = 0.0; d.ll_const_all = 0.0; d.kl_const = b;
     }
     lap("upload + data constants");
+    // fewer than four counts per cell on average: the kernel variant whose sparse rows skip the share machinery
+    z_sparse = (double)(data_sum / (long double)KG) < 4.0;
+    if (const char* e = getenv("BNMF_Z_SPARSE")) z_sparse = atoi(e) != 0;
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (z_config()) return 1; }
     if (mh_setup()) return 1;
     CK(cudaStreamSynchronize(stream));
@@ -613,7 +616,7 @@ struct Sampler : bnmf_handle {
 
   // ---- k_zstat dispatch over the compile-time signature count -------------------
   template <int NPV> int z_launch_t(bool configure) {
-    auto kern = k_zstat<T, NPV>;
+    auto kern = z_sparse ? k_zstat<T, NPV, true> : k_zstat<T, NPV, false>;
     if (configure) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem));
       return 0;

@@ -515,8 +515,13 @@ template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int NP,
 // (0.084 -> 0.03 ms; it is what a 12,500-genome shard of an 8-GPU run pays 8 times as dearly).  Mutation types
 // are visited in the order `korder` (descending total count, fixed at bnmf_create), so that the last items of a
 // column tile -- the tail of the launch -- are its lightest.
-template <typename T, int NP>
-__global__ void __launch_bounds__(32 * ZWarps<NP>::value, (NP <= 32 ? 2 : 1))
+template <typename T, int NP, bool SPARSE>
+#ifndef ZV_REGS
+#define ZV_REGS 96
+#endif
+// (96 registers: two of its blocks and a 256-thread block of the side stream's hyper-draw kernels share an SM's
+//  register file -- the overlap of section 4.2 of DESIGN.md needs all three resident)
+__global__ void __launch_bounds__(32 * ZWarps<NP>::value) __maxnreg__(NP <= 32 ? ZV_REGS : 168)
 k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA, int* work_ctr) {
   constexpr int NPAD = ZPad<NP>::value;
   constexpr int TR = zthr_rows(NP);
@@ -629,8 +634,9 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
       // Sparse rows (exome-like counts: a quad or two per cell): sharing out the row's quads costs more -- scan,
       // cell table, spilled-cell fix-up: ~300 instructions -- than the idle lanes it saves.  Every lane then draws
       // the picks of its own cell: its own threshold column, its own histogram column, nothing to fix up.
-      const int maxq = __reduce_max_sync(0xffffffffu, q);
-      if (32 * maxq <= __reduce_add_sync(0xffffffffu, q) + 80) {
+      // (SPARSE: a kernel variant of its own, chosen at bnmf_create for data with few counts per cell -- the extra
+      //  branch costs the dense kernel registers it needs to share an SM with the side stream's kernels)
+      if (SPARSE && 32 * __reduce_max_sync(0xffffffffu, q) <= __reduce_add_sync(0xffffffffu, q) + 80) {
         if (q > 0) {
           const unsigned long long cell = cell0 + (unsigned long long)k_this + (unsigned long long)((unsigned)K * (unsigned)lane);
           const uint32_t col = thr_sa + 4u * (unsigned)lane;
