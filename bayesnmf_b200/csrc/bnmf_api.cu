@@ -1020,7 +1020,7 @@ struct Sampler : bnmf_handle {
   int p_rows_launch();
   double* gram_part = nullptr; double* gram_buf = nullptr; int gram_chunks = 0;   // Normal likelihood: Gram-matrix P sweep
   int p_gram_launch();
-  int mhat_rebuild(); size_t eg_smem = 0; int eg_gb = 0;
+  int mhat_rebuild(); size_t eg_smem = 0; int eg_gb = 0; bool a_coop = false;
   unsigned char* tc_Pd = nullptr; int* tc_eP = nullptr; size_t tc_smem = 0;     // tensor-core Mhat (Normal likelihood): digit planes of P
   double* asum = nullptr; double sig_alpha = 3.0, sig_beta = 3.0;
 

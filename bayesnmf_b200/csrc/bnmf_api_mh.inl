@@ -66,6 +66,15 @@ template <typename T> int Sampler<T>::mh_setup() {
     const long long len = (long long)K * N + (long long)N * N;
     if (dalloc(&gram_part, (long long)gram_chunks * len) || dalloc(&gram_buf, len)) return 1;
   }
+  // rank learner: one cooperative launch when all its column blocks fit on the device at once (BNMF_A_COOP=0: a launch per signature)
+  if (cfg.learning_rank && !(getenv("BNMF_A_COOP") && atoi(getenv("BNMF_A_COOP")) == 0)) {
+    int per_sm = 0, sms = 148, coop = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg.device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_a_sweep<T>, 256, 0) == cudaSuccess)
+      a_coop = (long long)col_blocks <= (long long)per_sm * sms;
+    else cudaGetLastError();
+  }
   // Normal likelihood: the E sweep in Gram-matrix form (BNMF_EGRAM=0: k_e_sweep), when P fits in shared memory
   if (gram_buf && !(getenv("BNMF_EGRAM") && atoi(getenv("BNMF_EGRAM")) == 0)) {
     // genomes per block: the whole shard in one wave of two blocks per SM when that fits the shared memory (a
@@ -174,7 +183,19 @@ template <typename T> int Sampler<T>::p_rows_launch() {
 
 template <typename T> int Sampler<T>::rank_sweep_kernels(int* pending) {
   const int N = cfg.N;
-  k_r<T><<<1, 32, 0, stream>>>(d); mark("k_r"); ++launches;
+  k_r<T><<<1, 96, 0, stream>>>(d); mark("k_r"); ++launches;
+  if (world <= 1 && a_coop) {          // every column block resident at once: the N passes as one cooperative launch
+    CK(cudaMemsetAsync(red_ticket + 1, 0, sizeof(unsigned), stream));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)col_blocks); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0; lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&lc, k_a_sweep<T>, d, red_ticket + 1));
+    ++launches; mark("k_a_sweep");
+    *pending = N - 1;
+    return 0;
+  }
   for (int n = 0; n < N; ++n) {
     if (world <= 1) {     // nothing to exchange: the last block of the pass reduces and draws
       k_a_pass<T, 1><<<col_blocks, 256, 0, stream>>>(d, n, n ? n - 1 : -1, red_ticket + 1); mark("k_a_pass"); ++launches;

@@ -1054,17 +1054,21 @@ template <typename T> __device__ __forceinline__ double temperature(const Dev<T>
 }
 template <typename T>
 __global__ void k_r(Dev<T> d) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one thread per candidate rank r = 0..N (three pow() each: serial they are 20 us of an iteration at N = 10),
+  // then thread 0 walks the N + 1 weights in order -- the sums are those of the serial loop
+  __shared__ double probs[65];
   const int N = d.N, iter = d.ctrl->iter;
   const double Tm = temperature(d, iter);
   int sA = 0;
   for (int n = 0; n < N; ++n) sA += d.A[n];
-  double probs[65], tot = 0.0;
-  for (int r = 0; r <= N; ++r) {
+  for (int r = threadIdx.x; r <= N; r += blockDim.x) {
     const double q = prior_prob_1((double)r, N);
     probs[r] = (1.0 / (double)(N + 1)) * pow(pow(q, (double)sA) * pow(1.0 - q, (double)(N - sA)), Tm);
-    tot += probs[r];
   }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double tot = 0.0;
+  for (int r = 0; r <= N; ++r) tot += probs[r];
   const double u = u01<double>(make_stream(d.seed, iter, PUR_R, 0).at(0).x);
   double cdf = 0.0;
   int r = 0;
@@ -1178,6 +1182,77 @@ __device__ __forceinline__ void a_draw_block(const Dev<T>& d, int n, double l0, 
 template <typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_a_draw(Dev<T> d, int n, const double* lsum) {
   a_draw_block<T, THREADS>(d, n, lsum[0], lsum[1]);
+}
+
+// ------------------------------------------------------------------------------
+// k_a_sweep: the N passes of the rank learner (k_a_pass + its draw, above) as ONE cooperative launch for problems
+// whose column blocks are all resident at once (C2: 63 blocks): a pass, a grid barrier, block 0 folds the partials
+// in block order and draws A_n (a_draw_block), a grid barrier, the next signature.  Same sums in the same order as
+// the per-signature launches; what goes is 2/3 of their 12 us apiece (launch, ticket, tail).
+// `bar` counts arrivals (zeroed by the host before the launch); co-residency comes from the cooperative launch.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+  }
+  __syncthreads();
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_a_sweep(Dev<T> d, unsigned* bar) {
+  __shared__ double s0[32], s1[32];
+  __shared__ double scratch[8];
+  __shared__ double tot[2];
+  const int K = d.K, N = d.N;
+  const int WPB = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long g = (long long)blockIdx.x * WPB + wid;
+  const bool normal = d.likelihood == LIK_NORMAL;
+  unsigned phase = 0;
+  for (int n = 0; n < N; ++n) {
+    const int n_prev = n - 1;
+    double l0 = 0.0, l1 = 0.0;
+    if (g < d.G) {
+      const int An = d.A[n];
+      const double e = (double)d.E[n + (long long)N * g];
+      const double eprev = n_prev >= 0 ? (double)d.E[n_prev + (long long)N * g] : 0.0;
+      const double sg = normal ? (double)d.sigmasq[g] : 0.0;
+      for (int k = lane; k < K; k += 32) {
+        const long long i = k + (long long)K * g;
+        double mh = (double)d.Mhat[i];
+        if (n_prev >= 0) { mh = (double)(T)(mh + __ldcg(&d.dvec[k]) * eprev); d.Mhat[i] = (T)mh; }
+        const double pe = (double)d.P[k + (long long)K * n] * e;
+        const double mh0 = An ? mh - pe : mh, mh1 = An ? mh : mh + pe;
+        const double m = Mat(d, i);
+        if (normal) { l0 += dnorm_log(m, mh0, sg); l1 += dnorm_log(m, mh1, sg); }
+        else {
+          const double a = mh0 > 1e-6 ? mh0 : 1e-6, b = mh1 > 1e-6 ? mh1 : 1e-6;
+          l0 += m * log(a) - a; l1 += m * log(b) - b;
+        }
+      }
+    }
+    l0 = warp_sum(l0); l1 = warp_sum(l1);
+    if (lane == 0) { s0[wid] = l0; s1[wid] = l1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < WPB; ++w) { a += s0[w]; b += s1[w]; }
+      d.apart[2 * (long long)blockIdx.x] = a; d.apart[2 * (long long)blockIdx.x + 1] = b;
+    }
+    grid_barrier(bar, ++phase * gridDim.x);
+    if (blockIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) { a += __ldcg(&d.apart[2 * (long long)i]); b += __ldcg(&d.apart[2 * (long long)i + 1]); }
+      a = block_sum<256>(a, scratch);
+      b = block_sum<256>(b, scratch);
+      if (threadIdx.x == 0) { tot[0] = a; tot[1] = b; }
+      __syncthreads();
+      a_draw_block<T, 256>(d, n, tot[0], tot[1]);       // A[n], dvec
+    }
+    grid_barrier(bar, ++phase * gridDim.x);
+  }
 }
 
 // ------------------------------------------------------------------------------

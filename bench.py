@@ -83,6 +83,9 @@ def algorithmic_bytes(kernel, w, G, elem):
         "k_p_rows": (dm + 2 * elem) * KG + elem * NG,                    # M, Mhat in/out, E in
         "k_final": (dm + 2 * elem) * KG,
         "k_a_pass": (dm + 2 * elem) * KG,
+        "k_a_sweep": N * (dm + 2 * elem) * KG,                           # the N passes of the rank learner in one launch
+        "k_e_gram": dm * KG + 4 * elem * NG,                             # M once, E in/out + its two prior parameters
+        "k_mhat_tc": elem * KG + elem * (KN + NG),                       # Mhat out, P and E in
         "k_mhat_full": elem * KG + elem * (KN + NG),
         "k_gram_part": dm * KG + elem * NG,
         "k_p_gram": elem * KN,
