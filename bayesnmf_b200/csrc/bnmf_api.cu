@@ -276,7 +276,7 @@ struct Sampler : bnmf_handle {
   std::map<std::string, Hyper<T>*> hy;
   std::map<std::string, long long> hy_len;
   double* stage = nullptr; long long stage_len = 0;      // device double staging
-  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96; int ZR = 32, ZR_B = 2, z_ctB = 0; bool z_sparse = false;
+  int* work_ctr = nullptr; int n_ktiles = 1; int KT = 96; int ZR = 32, ZR_B = 2, z_ctB = 0; bool z_sparse = false, z_split = false;
   double* red_slices = nullptr; unsigned* red_ticket = nullptr;
   int* nanflags = nullptr;
   T* P_hist = nullptr; int32_t* A_hist = nullptr;
@@ -590,6 +590,9 @@ struct Sampler : bnmf_handle {
     // fewer than four counts per cell on average: the kernel variant whose sparse rows skip the share machinery
     z_sparse = (double)(data_sum / (long double)KG) < 4.0;
     if (const char* e = getenv("BNMF_Z_SPARSE")) z_sparse = atoi(e) != 0;
+    // fewer work items than half the resident warps: the variant in which 2, 4 or 8 warps share an item
+    z_split = !z_sparse && 2LL * d.n_zitems <= 148LL * 16;
+    if (const char* e = getenv("BNMF_Z_SPLIT")) z_split = !z_sparse && atoi(e) > 1;
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (z_config()) return 1; }
     if (mh_setup()) return 1;
     CK(cudaStreamSynchronize(stream));
@@ -616,7 +619,7 @@ struct Sampler : bnmf_handle {
 
   // ---- k_zstat dispatch over the compile-time signature count -------------------
   template <int NPV> int z_launch_t(bool configure) {
-    auto kern = z_sparse ? k_zstat<T, NPV, true> : k_zstat<T, NPV, false>;
+    auto kern = z_sparse ? k_zstat<T, NPV, 1> : z_split ? k_zstat<T, NPV, 2> : k_zstat<T, NPV, 0>;
     if (configure) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem));
       return 0;
@@ -628,9 +631,15 @@ struct Sampler : bnmf_handle {
     int bx = dev_sms * per_sm;
     const long long items = d.n_zitems;
     constexpr int ZW = ZWarps<NPV>::value;
-    long long need = (items + ZW - 1) / ZW;
+    // fewer items than resident warps: 2, 4 or 8 warps share an item (the dense kernel only)
+    int S = 1;
+    if (z_split) {
+      while (S < 8 && items * S * 2 <= (long long)bx * ZW) S *= 2;
+      if (const char* e = getenv("BNMF_Z_SPLIT")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) S = v; }
+    }
+    long long need = (items * S + ZW - 1) / ZW;
     if (bx > need) bx = (int)need;
-    kern<<<bx, 32 * ZW, z_smem, stream>>>(d, make_zkeys(d.seed), ZR, ZR_B, (int)((d.G + 31) / 32) - z_ctB, work_ctr); mark("k_zstat");
+    kern<<<bx, 32 * ZW, z_smem, stream>>>(d, make_zkeys(d.seed), ZR, ZR_B, (int)((d.G + 31) / 32) - z_ctB, (S == 8 ? 3 : S == 4 ? 2 : S == 2 ? 1 : 0), work_ctr); mark("k_zstat");
     return 0;
   }
   int z_dispatch(bool configure) {

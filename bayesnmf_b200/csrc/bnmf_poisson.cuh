@@ -515,14 +515,16 @@ template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int NP,
 // (0.084 -> 0.03 ms; it is what a 12,500-genome shard of an 8-GPU run pays 8 times as dearly).  Mutation types
 // are visited in the order `korder` (descending total count, fixed at bnmf_create), so that the last items of a
 // column tile -- the tail of the launch -- are its lightest.
-template <typename T, int NP, bool SPARSE>
+template <typename T, int NP, int MODE /* 0 dense, 1 sparse rows drawn lane-per-cell, 2 dense with several warps per item */>
 #ifndef ZV_REGS
 #define ZV_REGS 96
 #endif
 // (96 registers: two of its blocks and a 256-thread block of the side stream's hyper-draw kernels share an SM's
 //  register file -- the overlap of section 4.2 of DESIGN.md needs all three resident)
 __global__ void __launch_bounds__(32 * ZWarps<NP>::value) __maxnreg__(NP <= 32 ? ZV_REGS : 168)
-k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA, int* work_ctr) {
+k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA, int lgS_arg /* log2 of the warps per item (MODE 2) */, int* work_ctr) {
+  constexpr bool SPARSE = MODE == 1;
+  const int lgS = MODE == 2 ? lgS_arg : 0;
   constexpr int NPAD = ZPad<NP>::value;
   constexpr int TR = zthr_rows(NP);
   const int K = d.K, N = d.N, G = d.G;
@@ -560,9 +562,14 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
     const int n_warps = (int)gridDim.x * ZWarps<NP>::value;
     int next = (int)blockIdx.x * ZWarps<NP>::value + wid;
   for (;;) {
-    const int item = next;
-    if (item >= n_items) break;
+    // Small problems (fewer items than resident warps; the heaviest row-tile alone is 40 us of one warp at 96 x 100):
+    // S warps share an item -- each forms the row's thresholds itself and draws the S-th part of its quads into
+    // its own tables; the margins are integer atomics, so the result does not change.  Split 0 writes the metric
+    // partials of the item.
+    const int unit = next;
+    if (unit >= (n_items << lgS)) break;
     if (lane == 0) next = n_warps + atomicAdd(work_ctr, 1);      // the next ticket travels while this item is processed
+    const int item = unit >> lgS, split = unit - (item << lgS);
     // items in chunk-major order: chunk 0 (it holds the heaviest mutation types) of every column tile first, the
     // lightest chunk last -- longest processing time first, the warps that finish last are on the cheapest items
     // (a single row of the heaviest type over 32 genomes is ~8 rows' worth of picks: taken late it IS the tail)
@@ -605,7 +612,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
       T total = (T)0;
 #pragma unroll
       for (int n = 0; n < NP; ++n) total = add_rn<T>(total, mul_rn<T>(Prow[n], Esm[n * 32 + lane]));
-      if (valid) {
+      if (valid && split == 0) {
         const double mh = (double)total;
         const double lam = mh > 1e-6 ? mh : 1e-6;
         const double L = log(lam);
@@ -673,8 +680,11 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
       }
       __syncwarp();   // threshold columns and the cell table visible to the whole warp
       // ---- phase 2: an equal contiguous share [qd, qhi) of the row's quads per lane ----
-      int qd = (int)(((unsigned long long)lane * (unsigned)Tq) >> 5);
-      const int qhi = (int)(((unsigned long long)(lane + 1) * (unsigned)Tq) >> 5);
+      // this warp's part of the row (a row holds fewer than 2^27 quads: cells <= 2^24 counts)
+      const int q_lo = (int)(((unsigned long long)(unsigned)Tq * (unsigned)split) >> lgS);
+      const int q_n = (int)(((unsigned long long)(unsigned)Tq * (unsigned)(split + 1)) >> lgS) - q_lo;
+      int qd = q_lo + (int)(((unsigned long long)lane * (unsigned)q_n) >> 5);
+      const int qhi = q_lo + (int)(((unsigned long long)(lane + 1) * (unsigned)q_n) >> 5);
       // owner of the first quad: the cell c with excl[c] <= qd < excl[c] + q[c]
       int c_first = 0, ec_first = 0;
 #pragma unroll
@@ -684,7 +694,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
       }
       const bool F = ec_first < qd;                  // the first cell started in an earlier lane's share
       {
-        const bool dense = Tq >= 96;                 // rows of mostly full quads: branch-free searches
+        const bool dense = q_n >= 96;                // rows of mostly full quads: branch-free searches
         uint32_t da = desc_sa + 16u * (unsigned)(c_first - 1);
         int ec = 0, nxt = qd, mc = 0;                // qd >= nxt: the first pass loads the first cell
         bool spill = F;                              // first cell of a spilled share -> cont[.][lane]
@@ -770,7 +780,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
     }
     // per-item metric partials, fixed reduction order
     a_sse = warp_sum(a_sse); a_kl = warp_sum(a_kl); a_ll = warp_sum(a_ll);
-    if (lane == 0) {
+    if (lane == 0 && split == 0) {
       double* zp = d.zpart + (long long)item * PC_COLS;
       zp[PC_SSE] = a_sse; zp[PC_KLV] = a_kl; zp[PC_LLV] = a_ll; zp[PC_LP_E] = 0.0; zp[PC_EACC] = 0.0;
     }
