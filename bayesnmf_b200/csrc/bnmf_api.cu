@@ -958,6 +958,13 @@ struct Sampler : bnmf_handle {
     static const bool off = getenv("BNMF_OVERLAP") && !strcmp(getenv("BNMF_OVERLAP"), "0");
     return !off && side != nullptr && cfg.prior == BNMF_GAMMA && cfg.likelihood == BNMF_POISSON && !cfg.MH && !graphs_allowed();
   }
+  // within-iteration fork of the two sides' hyper-draws (graph-replayed problems, gamma prior); the list of parked
+  // Alpha_e cells is allocated by ensure_graph() before the capture starts
+  bool fork_hyper() const {
+    static const bool off = getenv("BNMF_FORK_HYPER") && !strcmp(getenv("BNMF_FORK_HYPER"), "0");
+    return !off && side != nullptr && alpha_retry != nullptr && !prof_on && graphs_allowed() &&
+           cfg.prior == BNMF_GAMMA && cfg.likelihood == BNMF_POISSON && !cfg.MH;
+  }
   int mh_setup();
   int mh_iteration(int from_prior, uint32_t have);
   int poisson_iteration(int from_prior, uint32_t have, cudaEvent_t z0, cudaEvent_t z1) {
@@ -969,7 +976,26 @@ struct Sampler : bnmf_handle {
               k_eside<T, ET, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside"); break;
       case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
               k_eside<T, ET, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside"); break;
-      case 2: if (hyper_ready) {          // Beta_p / Alpha_p of this iteration were drawn under the previous k_zstat
+      case 2: if (!hyper_ready && fork_hyper()) {
+                // Small problems (the iteration replayed as a CUDA graph, no overlap across iterations): the hyper-draws of
+                // the two sides read nothing of each other -- the E side's run on the side stream (a parallel branch of
+                // the graph) while the P side's and the draw of P run here; the draw of E joins them.  The kernels take
+                // the iteration number from the device's counter (a graph freezes kernel arguments).
+                CK(cudaEventRecord(ev_fork, stream));
+                CK(cudaStreamWaitEvent(side, ev_fork, 0));
+                const long long ncell = (long long)cfg.N * cfg.G;
+                CK(cudaMemsetAsync(alpha_n_retry, 0, sizeof(int), side));
+                k_eside_hyper<T, 256><<<blocks(ncell, 256), 256, 0, side>>>(d, -1, alpha_retry, alpha_n_retry, alpha_cap);
+                k_alpha_retry<T><<<blocks((alpha_cap + ALPHA_RETRY_PER_WARP - 1) / ALPHA_RETRY_PER_WARP, 8), 256, 0, side>>>(d, -1, alpha_retry, alpha_n_retry, alpha_cap);
+                CK(cudaEventRecord(ev_join, side));
+                k_pside_hyper<T, 128><<<cfg.N, 128, 0, stream>>>(d, -1); mark("k_pside_hyper");
+                k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
+                CK(cudaStreamWaitEvent(stream, ev_join, 0));
+                k_eside<T, ET, PRIOR_GAMMA, 0, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside");
+                launches += 3;
+                break;
+              }
+              if (hyper_ready) {          // Beta_p / Alpha_p of this iteration were drawn under the previous k_zstat
                 CK(cudaStreamWaitEvent(stream, ev_join_p, 0));
                 k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
               } else k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
@@ -1143,6 +1169,13 @@ struct Sampler : bnmf_handle {
   int ensure_graph(bool wantP, bool wantA) {
     const int key = (h_converged ? 1 : 0) | (wantP ? 2 : 0) | (wantA ? 4 : 0);
     if (gexec && gkey == key) return 0;
+    if (!alpha_retry && cfg.prior == BNMF_GAMMA && cfg.likelihood == BNMF_POISSON && !cfg.MH) {     // (fork_hyper)
+      const long long ncell = (long long)cfg.N * cfg.G;
+      alpha_cap = (int)std::max<long long>(256, std::min<long long>(ncell / 4 + 1024, 1LL << 30));
+      if (const char* e = getenv("BNMF_ALPHA_CAP")) { const int v = atoi(e); if (v >= 1) alpha_cap = v; }
+      if (dalloc(&alpha_retry, (long long)BNMF_ALPHA_ENV_COLS * alpha_cap) || dalloc(&alpha_n_retry, 1)) return 1;
+      CK(cudaStreamSynchronize(stream));
+    }
     if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
     cudaGraph_t g = nullptr;
     const int before = launches;

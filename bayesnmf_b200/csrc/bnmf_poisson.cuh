@@ -72,7 +72,8 @@ __global__ void k_begin_iter(Dev<T> d, int* work_ctr, int n_ctr) {
 // stream under the previous k_zstat, which takes two of the three samplers of k_pside off the
 // critical path of an iteration (one block per signature: pure latency).
 template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_pside_hyper(Dev<T> d, int iter) {
+__global__ void __launch_bounds__(THREADS) k_pside_hyper(Dev<T> d, int iter_arg) {
+  const int iter = iter_arg < 0 ? d.ctrl->iter : iter_arg;      // < 0: the iteration under way (launches replayed from a graph)
   const int n = blockIdx.x, K = d.K;
   for (int k = threadIdx.x; k < K; k += THREADS) {
     const long long c = (long long)k + (long long)K * n;
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
 #define BNMF_ALPHA_ENV_COLS 21
 template <typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
-k_eside_hyper(Dev<T> d, int iter, double* __restrict__ retry, int* __restrict__ n_retry, int cap) {
+k_eside_hyper(Dev<T> d, int iter_arg, double* __restrict__ retry, int* __restrict__ n_retry, int cap) {
+  const int iter = iter_arg < 0 ? d.ctrl->iter : iter_arg;
   const long long cells = (long long)d.N * d.G;
   const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
   const long long ii = idx < cells ? idx : cells - 1;     // the whole block runs the staged sampler (its barriers)
@@ -237,7 +239,8 @@ __device__ __forceinline__ void alpha_env_load(const Dev<T>& d, int iter, const 
   st = make_stream(d.seed, iter, PUR_HYP_E2, c);
 }
 template <typename T>
-__global__ void __launch_bounds__(256) k_alpha_retry(Dev<T> d, int iter, const double* __restrict__ retry, const int* __restrict__ n_retry, int cap) {
+__global__ void __launch_bounds__(256) k_alpha_retry(Dev<T> d, int iter_arg, const double* __restrict__ retry, const int* __restrict__ n_retry, int cap) {
+  const int iter = iter_arg < 0 ? d.ctrl->iter : iter_arg;
   const int n = min(*n_retry, cap);
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
