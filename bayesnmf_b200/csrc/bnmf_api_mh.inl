@@ -236,8 +236,17 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
     if (mhat_rebuild()) return 1;
     k_final<T><<<col_blocks, 256, 0, stream>>>(d, -1, (have & BNMF_HAVE_SIGMASQ) ? 1 : 0); mark("k_final"); ++launches;
   } else {
+    // the E side's prior parameters (they read E only) are not needed before the E sweep: a parallel branch, on the
+    // side stream, under the P sweep
+    const bool fork_e = side != nullptr && !prof_on;
+    if (fork_e) {
+      CK(cudaEventRecord(ev_fork, stream));
+      CK(cudaStreamWaitEvent(side, ev_fork, 0));
+      k_hyper<T><<<blocks(NG, 128), 128, 0, side>>>(d, 1);
+      CK(cudaEventRecord(ev_join, side));
+    }
     k_hyper<T><<<blocks(KN, 128), 128, 0, stream>>>(d, 0); mark("k_hyper");
-    k_hyper<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1); mark("k_hyper");
+    if (!fork_e) { k_hyper<T><<<blocks(NG, 128), 128, 0, stream>>>(d, 1); mark("k_hyper"); }
     launches += 2;
     if (!gram_buf) { if (mhat_rebuild()) return 1; }   // (the Gram-matrix P sweep rebuilds Mhat after itself)
     const dim3 pgrid(d.n_gchunks, p_ktiles), pblock(p_kx, p_gy);
@@ -255,6 +264,7 @@ template <typename T> int Sampler<T>::mh_iteration(int from_prior, uint32_t have
         launches += 2;
       }
     }
+    if (fork_e) CK(cudaStreamWaitEvent(stream, ev_join, 0));
     if (gram_buf && eg_smem) {       // Normal likelihood: both sweeps through Gram matrices, Mhat from the tensor cores afterwards
       k_e_gram<T><<<(unsigned)((G + eg_gb - 1) / eg_gb), EG_T, eg_smem, stream>>>(d, eg_gb); mark("k_e_gram"); ++launches;
       if (mhat_rebuild()) return 1;

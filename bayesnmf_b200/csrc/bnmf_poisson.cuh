@@ -846,12 +846,29 @@ __global__ void __launch_bounds__(THREADS) k_reduce_partials(Dev<T> d, double* s
   const long long total = (long long)d.n_zitems + d.n_eblocks;
   const long long per = (total + gridDim.x - 1) / gridDim.x;
   const long long lo = per * blockIdx.x, hi = lo + per < total ? lo + per : total;
-  for (int c = 0; c < PC_COLS; ++c) {
-    double v = 0.0;
-    for (long long i = lo + threadIdx.x; i < hi; i += THREADS)
-      v += i < d.n_zitems ? d.zpart[i * PC_COLS + c] : d.epart[(i - d.n_zitems) * PC_COLS + c];
-    const double s = block_sum<THREADS>(v, scratch);
-    if (threadIdx.x == 0) slices[blockIdx.x * PC_COLS + c] = s;
+  {   // one pass over the slice for all PC_COLS columns (the sums and their order are those of a pass per column)
+    __shared__ double wsum[THREADS / 32][PC_COLS];
+    double v[PC_COLS];
+#pragma unroll
+    for (int c = 0; c < PC_COLS; ++c) v[c] = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += THREADS) {
+      const double* row = i < d.n_zitems ? d.zpart + i * PC_COLS : d.epart + (i - d.n_zitems) * PC_COLS;
+#pragma unroll
+      for (int c = 0; c < PC_COLS; ++c) v[c] += row[c];
+    }
+#pragma unroll
+    for (int c = 0; c < PC_COLS; ++c) v[c] = warp_sum(v[c]);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int c = 0; c < PC_COLS; ++c) wsum[threadIdx.x >> 5][c] = v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < PC_COLS) {
+      double r = 0.0;
+#pragma unroll
+      for (int w = 0; w < THREADS / 32; ++w) r += wsum[w][threadIdx.x];
+      slices[blockIdx.x * PC_COLS + threadIdx.x] = r;
+    }
   }
   __threadfence();
   __syncthreads();
