@@ -170,6 +170,28 @@ constexpr int ET = 512;   // threads per block of k_eside
 enum StType { ST_T, ST_I32, ST_U64 };
 struct StEntry { void* p; long long len; StType ty; };
 
+// Process-wide pool of the small pinned buffers handles fetch their metric rows into: cudaMallocHost costs
+// 0.5 - 2 ms apiece, more than the rest of bnmf_create for a shard; a closed handle leaves its buffer here.
+static std::mutex g_hpin_mutex;
+static std::vector<std::pair<void*, size_t>> g_hpin_pool;
+static cudaError_t pinned_get(void** p, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_hpin_mutex);
+    for (size_t i = 0; i < g_hpin_pool.size(); ++i)
+      if (g_hpin_pool[i].second == bytes) { *p = g_hpin_pool[i].first; g_hpin_pool.erase(g_hpin_pool.begin() + i); return cudaSuccess; }
+  }
+  return cudaMallocHost(p, bytes);
+}
+static void pinned_put(void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_hpin_mutex);
+  if (g_hpin_pool.size() < 64) g_hpin_pool.push_back({p, bytes}); else cudaFreeHost(p);
+}
+static void pinned_release_all() {
+  std::lock_guard<std::mutex> lk(g_hpin_mutex);
+  for (auto& b : g_hpin_pool) cudaFreeHost(b.first);
+  g_hpin_pool.clear();
+}
+
 // process-wide pinned staging buffer for the upload of count matrices (bnmf_create)
 static std::mutex g_pin_mutex;
 static void* g_pin = nullptr;
@@ -305,7 +327,7 @@ struct Sampler : bnmf_handle {
     if (stream) cudaStreamSynchronize(stream);
     if (side) cudaStreamSynchronize(side);
     for (auto& a : allocs) cached_free(a.first, a.second, cfg.device);
-    if (h_metrics) cudaFreeHost(h_metrics);
+    if (h_metrics) pinned_put(h_metrics, (size_t)d.metrics_cap * MC_COLS * sizeof(double));
     for (auto e : zev) cudaEventDestroy(e);
     for (auto e : iev) cudaEventDestroy(e);
     if (flush_buf) cudaFree(flush_buf);
@@ -454,7 +476,7 @@ struct Sampler : bnmf_handle {
     if (dalloc(&d.ctrl, 1) || dalloc(&red_slices, RED_BLOCKS * PC_COLS) || dalloc(&red_ticket, 2)) return 1;
     d.metrics_cap = 256;
     if (dalloc(&d.metrics, (long long)d.metrics_cap * MC_COLS)) return 1;
-    CK(cudaMallocHost((void**)&h_metrics, (size_t)d.metrics_cap * MC_COLS * sizeof(double)));
+    CK(pinned_get((void**)&h_metrics, (size_t)d.metrics_cap * MC_COLS * sizeof(double)));
     if (dalloc(&P_hist, (long long)d.metrics_cap * KN) || dalloc(&A_hist, (long long)d.metrics_cap * N)) return 1;
     { double* t; if (dalloc(&t, 1)) return 1; d.temps = t; d.n_temps = 0; }
     // ring
@@ -681,6 +703,14 @@ struct Sampler : bnmf_handle {
     // handle; the captured graph keeps its pointer); a change of shape takes a new array from the slab
     const bool same_shape = (it->second->is_matrix != 0) == (n != 1);
     T* p = const_cast<T*>(it->second->p);
+    if (n == 1 && same_shape) {
+      // a scalar over a scalar (the defaults, the usual overrides): one stream-ordered 8-byte copy, no staging, no
+      // synchronisation (a pageable source is staged by the driver before the call returns; kernels launched later
+      // on this stream -- and, through the fork event, on the side stream -- see the new value)
+      const T hv = (T)v[0];
+      CK(cudaMemcpyAsync(p, &hv, sizeof(T), cudaMemcpyHostToDevice, stream));
+      return 0;
+    }
     if (!same_shape) { if (dalloc(&p, n)) return 1; }
     if (ensure_stage(n)) return 1;
     CK(cudaStreamSynchronize(stream));
@@ -1427,6 +1457,7 @@ int bnmf_release_cached_memory(void) {
     std::lock_guard<std::mutex> lk(g_pin_mutex);
     if (g_pin) { cudaFreeHost(g_pin); g_pin = nullptr; g_pin_bytes = 0; }
   }
+  pinned_release_all();
   return release_cached_blocks(-1);
 }
 
