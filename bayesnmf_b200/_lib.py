@@ -141,7 +141,7 @@ class Handle:
             "P": (self.K, self.N), "E": (self.N, self.G), "A": (self.N,), "R": (1,), "sigmasq": (self.G,),
             "SP": (self.K, self.N), "SE": (self.N, self.G), "Alpha": (self.G,), "Beta": (self.G,),
             "P_acceptance_rate": (self.K, self.N), "E_acceptance_rate": (self.N, self.G),
-            "Mhat": (self.K, self.G), "rowsumE": (self.N,),
+            "Mhat": (self.K, self.G), "rowsumE": (self.N,), "data_sum": (1,),
         }
         for nm in ("Mu", "Sigmasq", "Lambda", "Alpha", "Beta"):
             self.shapes[nm + "_p"] = (self.K, self.N)

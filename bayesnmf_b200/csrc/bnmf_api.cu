@@ -313,6 +313,7 @@ struct Sampler : bnmf_handle {
   bool time_z = true;
   double last_total_ms = 0, last_z_ms = 0; int64_t last_launches = 0;
   bool have_temps = false; int64_t temps_cap = 0;
+  double h_data_sum = 0.0;
   std::vector<double> h_temps;                             // host copy of the temperature schedule (bnmf_run)
   std::vector<double> h_rows;                              // every sample_metrics row so far, MC_COLS each (bnmf_run's windows)
   struct RunState {                                        // check_convergence_'s part of self$state (bnmf_run)
@@ -566,6 +567,7 @@ struct Sampler : bnmf_handle {
     }
     long double data_sum = 0.0L;
     for (long long c = 0; c < n_ch; ++c) data_sum += ch_sum[(size_t)c];
+    h_data_sum = (double)data_sum;
     lap("host pass over data");
     if (pois) {
       for (long long c = 0; c < n_ch; ++c) if (ch_cuda[(size_t)c]) return fail("bnmf_create: upload of the counts: %s", cudaGetErrorString((cudaError_t)ch_cuda[(size_t)c]));
@@ -788,6 +790,11 @@ struct Sampler : bnmf_handle {
   }
   int get_state(const char* name, double* out, int64_t len) override {
     CK(cudaSetDevice(cfg.device));
+    if (!strcmp(name, "data_sum")) {          // sum of this handle's data (what mean(data) of a sharded matrix is made of)
+      if (len != 1) return fail("bnmf_get_state: 'data_sum' is a scalar");
+      out[0] = h_data_sum;
+      return 0;
+    }
     if (!strcmp(name, "rowsumE")) {
       if (len != cfg.N) return fail("bnmf_get_state: 'rowsumE' has %d elements", cfg.N);
       std::vector<long long> h(cfg.N);

@@ -19,9 +19,11 @@ def _dev(dist):
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
-def global_mean(M_local, dist=None):
-    """mean(data) over all shards (the hyperprior defaults of R/setup.R:123-181 depend on it)."""
-    s, n = float(np.sum(M_local, dtype=np.float64)), float(np.size(M_local))
+def global_mean(M_local, dist=None, local_sum=None):
+    """mean(data) over all shards (the hyperprior defaults of R/setup.R:123-181 depend on it).  `local_sum`: the
+    shard's sum when the caller has it already (bnmf_create adds the data up while it converts them)."""
+    s = float(np.sum(M_local, dtype=np.float64)) if local_sum is None else float(local_sum)
+    n = float(np.size(M_local))
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return s / n
     import torch
@@ -53,7 +55,7 @@ def sharded_handle(M, N, dist, device=0, hyperprior_params=None, share_comm=None
     if world > 1 or hyperprior_params:
         # (a single unsharded handle without user values keeps the defaults bnmf_create installed from
         #  the mean of its own -- that is, of all -- columns: R/setup.R:123-181)
-        mean = global_mean(M[:, lo:hi], dist)
+        mean = global_mean(M[:, lo:hi], dist, local_sum=h.get_state("data_sum")[0])
         for name, value in fill_hyperprior_params(hyperprior_params, kw.get("prior", "gamma"), mean, N).items():
             if np.ndim(value) == 2 and name.endswith("_e"):
                 value = np.asarray(value)[:, lo:hi]

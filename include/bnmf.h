@@ -87,6 +87,7 @@ int bnmf_set_hyper(bnmf_handle* h, const char* name, const double* v, int64_t ro
  * "Lambda_p","Alpha_p","Beta_p" (K x N); "Mu_e",...,"Beta_e" (N x G); "Alpha","Beta"
  * (G, sigmasq prior).  Statistics replacing Z: "SP" = sum_g Z (K x N), "SE" = sum_k Z
  * (N x G).  "P_acceptance_rate" (K x N), "E_acceptance_rate" (N x G), "Mhat" (K x G).
+ * Read-only: "rowsumE" (N; also settable: the fixed-point row sums of E), "data_sum" (1: the sum of this handle's data).
  * NaN entries in a prior parameter mean "draw this column from the hyperprior"
  * (R/sample_priors.R:33-60). */
 int bnmf_set_state(bnmf_handle* h, const char* name, const double* v, int64_t len);

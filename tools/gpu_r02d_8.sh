@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-TAG=r02d
+TAG=${TAG:-r02f}
 run() { # N, workload, extra env
   env $3 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $1 --steps 50 --warmup 5 --no-cpu-baseline --workload $2 2> gpurun_out/bench_$2_n$1_$TAG.err > gpurun_out/bench_$2_n$1_$TAG.json
   python - <<PY
@@ -9,5 +9,3 @@ PY
 }
 run 8 c3 A=1
 run 4 c3 A=1
-run 8 c5 A=1
-run 8 c4 A=1
