@@ -130,6 +130,21 @@ static __global__ void k_cvt_in_u64(const double* src, unsigned long long* dst, 
   if (i < n) dst[i] = (unsigned long long)llrint(src[i]);
 }
 // data constants of the Poisson likelihood / padded KL (R/utils.R:103, :467-471)
+// genome-major copy of the counts (32 x 32 tiles through shared memory, both sides coalesced)
+static __global__ void k_transpose_counts(const int32_t* __restrict__ in, int32_t* __restrict__ out, int K, long long G) {
+  __shared__ int32_t tile[32][33];
+  const long long g0 = (long long)blockIdx.x * 32;
+  const int k0 = (int)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int k = k0 + (int)threadIdx.x; const long long g = g0 + j;
+    tile[j][threadIdx.x] = (k < K && g < G) ? in[k + (long long)K * g] : 0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int k = k0 + j; const long long g = g0 + threadIdx.x;
+    if (k < K && g < G) out[g + G * (long long)k] = tile[threadIdx.x][j];
+  }
+}
 static __global__ void k_data_consts(const int32_t* Mi, long long n, double* out /*2*/) {
   __shared__ double sc[8];
   double ll = 0.0, kl = 0.0;
@@ -474,7 +489,7 @@ struct Sampler : bnmf_handle {
     d.n_eblocks = (cfg.MH || cfg.likelihood == BNMF_NORMAL) ? (int)((G + 7) / 8) : blocks(NG, ET);
     if (dalloc(&d.zpart, (long long)d.n_zitems * PC_COLS + 2 * N) || dalloc(&d.epart, (long long)d.n_eblocks * PC_COLS) ||
         dalloc(&d.red, PC_COLS) || dalloc(&work_ctr, n_ktiles + 8) || dalloc(&nanflags, 5 * N)) return 1;
-    if (dalloc(&d.ctrl, 1) || dalloc(&red_slices, RED_BLOCKS * PC_COLS) || dalloc(&red_ticket, 2)) return 1;
+    if (dalloc(&d.ctrl, 1) || dalloc(&red_slices, RED_BLOCKS * PC_COLS) || dalloc(&red_ticket, 3)) return 1;
     d.metrics_cap = 256;
     if (dalloc(&d.metrics, (long long)d.metrics_cap * MC_COLS)) return 1;
     CK(pinned_get((void**)&h_metrics, (size_t)d.metrics_cap * MC_COLS * sizeof(double)));
@@ -572,6 +587,11 @@ struct Sampler : bnmf_handle {
     if (pois) {
       for (long long c = 0; c < n_ch; ++c) if (ch_cuda[(size_t)c]) return fail("bnmf_create: upload of the counts: %s", cudaGetErrorString((cudaError_t)ch_cuda[(size_t)c]));
       d.Mi = mi;
+      if (!cfg.MH) {   // k_zstat reads the counts genome-major
+        int32_t* mt; if (dalloc(&mt, KG)) return 1;
+        k_transpose_counts<<<dim3((unsigned)((G + 31) / 32), (unsigned)((K + 31) / 32)), dim3(32, 8), 0, stream>>>(mi, mt, K, (long long)G);
+        d.Mt = mt;
+      }
       {   // mutation types by descending total count (ties: by index): heavy rows first, the tail of a launch is light
         std::vector<double> rs((size_t)K, 0.0);
         for (long long c = 0; c < n_ch; ++c) for (int k = 0; k < K; ++k) rs[k] += ch_row[(size_t)c * K + k];
@@ -1004,12 +1024,14 @@ struct Sampler : bnmf_handle {
   }
   int mh_setup();
   int mh_iteration(int from_prior, uint32_t have);
-  int poisson_iteration(int from_prior, uint32_t have, cudaEvent_t z0, cudaEvent_t z1) {
+  int poisson_iteration(int from_prior, uint32_t have, cudaEvent_t z0, cudaEvent_t z1, bool fold_begin = false) {
+    // fold_begin: k_pside is also k_begin_iter (see the kernel)
+    int* const bc = fold_begin ? work_ctr : nullptr; const int bn = n_ktiles; unsigned* const bt = red_ticket + 2;
     const int keepP = (have & BNMF_HAVE_P) ? 1 : 0, keepE = (have & BNMF_HAVE_E) ? 1 : 0;
     // instantiated per (prior, prior draw or not): halves the code each launch has to fetch
     const int var = (cfg.prior == BNMF_GAMMA ? 2 : 0) | (from_prior ? 1 : 0);
     switch (var) {
-      case 0: k_pside<T, 128, PRIOR_EXPONENTIAL, 0><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
+      case 0: k_pside<T, 128, PRIOR_EXPONENTIAL, 0><<<cfg.N, 128, 0, stream>>>(d, keepP, bc, bn, bt); mark("k_pside");
               k_eside<T, ET, PRIOR_EXPONENTIAL, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside"); break;
       case 1: k_pside<T, 128, PRIOR_EXPONENTIAL, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
               k_eside<T, ET, PRIOR_EXPONENTIAL, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside"); break;
@@ -1034,8 +1056,8 @@ struct Sampler : bnmf_handle {
               }
               if (hyper_ready) {          // Beta_p / Alpha_p of this iteration were drawn under the previous k_zstat
                 CK(cudaStreamWaitEvent(stream, ev_join_p, 0));
-                k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
-              } else k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP); mark("k_pside");
+                k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP, bc, bn, bt); mark("k_pside");
+              } else k_pside<T, 128, PRIOR_GAMMA, 0><<<cfg.N, 128, 0, stream>>>(d, keepP, bc, bn, bt); mark("k_pside");
               if (hyper_ready) {          // ... and so were Beta_e / Alpha_e
                 CK(cudaStreamWaitEvent(stream, ev_join, 0));
                 k_eside<T, ET, PRIOR_GAMMA, 0, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside");
@@ -1194,8 +1216,11 @@ struct Sampler : bnmf_handle {
   }
   int launch_iteration(bool wantP, bool wantA, cudaEvent_t z0, cudaEvent_t z1) {
     const long long KN = (long long)cfg.K * cfg.N;
-    k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); mark("k_begin_iter"); ++launches;
-    if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (poisson_iteration(0, 0, z0, z1)) return 1; }
+    // (iterations replayed from a graph keep k_begin_iter: their side-branch kernels read the device's counter)
+    static const bool nofold = getenv("BNMF_FOLD_BEGIN") && !strcmp(getenv("BNMF_FOLD_BEGIN"), "0");
+    const bool fold_begin = !nofold && cfg.likelihood == BNMF_POISSON && !cfg.MH && !graphs_allowed();
+    if (!fold_begin) { k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); mark("k_begin_iter"); ++launches; }
+    if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (poisson_iteration(0, 0, z0, z1, fold_begin)) return 1; }
     else { if (mh_iteration(0, 0)) return 1; }
     if (finish_iteration()) return 1;
     if (wantP || wantA) {

@@ -87,13 +87,16 @@ __global__ void __launch_bounds__(THREADS) k_pside_hyper(Dev<T> d, int iter_arg)
 }
 
 template <typename T, int THREADS, int PRIOR, int FROM_PRIOR, int HYPER_DONE = 0>
-__global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
+__global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP, int* begin_ctr = nullptr, int n_ctr = 0, unsigned* begin_ticket = nullptr) {
   constexpr int from_prior = FROM_PRIOR || HYPER_DONE;      // (hyper-draws already made: take them as stored)
   constexpr int prior_draw_only = FROM_PRIOR;
   __shared__ double scratch[THREADS / 32];
   const int n = blockIdx.x;
   const int K = d.K, N = d.N;
-  const int iter = d.ctrl->iter;
+  // begin_ctr != nullptr: this launch is also k_begin_iter (one launch less on the chain of an iteration that is
+  // not replayed from a graph): every block works on iteration ctrl->iter + 1, the last one to finish does what
+  // k_begin_iter does -- by then every block has read the counter
+  const int iter = d.ctrl->iter + (begin_ctr ? 1 : 0);
   const int An = d.A[n];
   const double rsE = (double)d.rowsumE_fx[n] / RS_FX;
   double csum = 0.0, lp = 0.0;
@@ -145,6 +148,15 @@ __global__ void __launch_bounds__(THREADS) k_pside(Dev<T> d, int keepP) {
     d.rowsumE_fx[n] = 0ll;
     // deterministic: each block owns slot n of a small array folded by k_reduce_partials
     d.zpart[(long long)(d.n_zitems) * PC_COLS + n] = lps;
+  }
+  if (begin_ctr) {
+    __shared__ bool last;
+    if (threadIdx.x == 0) { __threadfence(); last = atomicAdd(begin_ticket, 1u) == gridDim.x - 1; }
+    __syncthreads();
+    if (!last) return;
+    for (int i = threadIdx.x; i < n_ctr; i += THREADS) begin_ctr[i] = 0;
+    for (int j = threadIdx.x; j < N; j += THREADS) { d.nzP[j] = 0; d.nzE[(iter & 1) * N + j] = 0; }
+    if (threadIdx.x == 0) { d.ctrl->iter = iter; d.ctrl->row += 1; *d.lp_P = 0.0; *d.pacc_sum = 0.0; *begin_ticket = 0u; }
   }
 }
 
@@ -501,10 +513,30 @@ __device__ __forceinline__ void zstat_quad(const U4& w, uint32_t col, const ZPiv
   }
 }
 
+// Fix-up pass of a dense row (see k_zstat): the counts a lane drew for a cell that began in an earlier lane's share
+// (cont[.][lane]) are summed over the consecutive lanes that continue the same cell -- a segmented shuffle
+// reduction of LEVELS doubling steps, `run` = lanes behind this one on the same cell -- and added to the cell's
+// histogram column by the first of them.
+template <int NP, int LEVELS>
+__device__ __forceinline__ void zstat_fixup(int* cont, int* hist, int lane, bool F, bool head, int run, int c_first) {
+#pragma unroll
+  for (int n = 0; n < NP; ++n) {
+    int v = cont[n * 32 + lane];
+    if (F) cont[n * 32 + lane] = 0;
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l) {
+      const int t = __shfl_down_sync(0xffffffffu, v, 1 << l);
+      if ((1 << l) <= run) v += t;
+    }
+    if (head && v) hist[n * 32 + c_first] += v;
+  }
+}
+
 // shared memory of k_zstat in bytes (host and device agree on it): per warp
-// { E tile (T), thr, hist, cont (int), cell descriptors, the row of P (T) }; nothing is shared between the warps
+// { E tile (T; a genome's column padded to NP + 1), thr, hist, cont (int), cell descriptors, the row of P (T) }; nothing is
+// shared between the warps
 template <typename T> __host__ __device__ inline size_t zstat_warp_bytes(int NP) {
-  return (size_t)32 * (zthr_rows(NP) + 2 * NP) * sizeof(int) + (size_t)32 * NP * sizeof(T) + 136 * sizeof(int) + (size_t)NP * sizeof(T);
+  return (size_t)32 * (zthr_rows(NP) + 2 * NP) * sizeof(int) + (size_t)32 * (NP + 1) * sizeof(T) + 136 * sizeof(int) + (size_t)NP * sizeof(T);
 }
 template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int NP, int W) {
   return (size_t)W * zstat_warp_bytes<T>(NP);
@@ -518,6 +550,12 @@ template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int NP,
 // (0.084 -> 0.03 ms; it is what a 12,500-genome shard of an 8-GPU run pays 8 times as dearly).  Mutation types
 // are visited in the order `korder` (descending total count, fixed at bnmf_create), so that the last items of a
 // column tile -- the tail of the launch -- are its lightest.
+// counts of genome g (local), mutation type k: the genome-major copy (a row of 32 genomes is one line)
+#ifdef BNMF_Z_NO_MT
+#define ZM(g, k) d.Mi[(long long)(k) + (long long)K * (g)]
+#else
+#define ZM(g, k) d.Mt[(long long)(g) + (long long)G * (k)]
+#endif
 template <typename T, int NP, int MODE /* 0 dense, 1 sparse rows drawn lane-per-cell, 2 dense with several warps per item */>
 #ifndef ZV_REGS
 #define ZV_REGS 96
@@ -533,8 +571,13 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
   const int K = d.K, N = d.N, G = d.G;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   unsigned char* wtabs = smem_raw;
-  T* Esm = reinterpret_cast<T*>(wtabs + (size_t)wid * zstat_warp_bytes<T>(NP));   // [NP][32 cells]  E tile of the item
-  uint32_t* thr = reinterpret_cast<uint32_t*>(Esm + NP * 32);       // [TR][32 cells]  pick thresholds of the row
+  // E tile of the item as it lies in global memory -- genome by genome --, a genome's column padded to the odd length
+  // ES: the tile is copied with coalesced loads (it is N * 32 contiguous elements; a load per lane and signature
+  // touched 32 sectors and held up the shared-memory traffic of every other warp of the SM behind it) and lane
+  // c reads its column Esm[c * ES + n] conflict-free
+  constexpr int ES = NP + 1;
+  T* Esm = reinterpret_cast<T*>(wtabs + (size_t)wid * zstat_warp_bytes<T>(NP));   // [32 cells][ES]
+  uint32_t* thr = reinterpret_cast<uint32_t*>(Esm + ES * 32);       // [TR][32 cells]  pick thresholds of the row
   int* hist = reinterpret_cast<int*>(thr) + TR * 32;                // [NP][32 cells]  counts of the item so far (its SE)
   int* cont = hist + NP * 32;                                       // [NP][32 lanes]  counts of a share's spilled first cell
   // cell descriptors of the current row: {first quad, picks, Philox counter words 0,1}; entry 32 = {all quads}
@@ -546,6 +589,9 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
   asm volatile("mov.u32 %0, %0;" : "+r"(thr_sa));
   asm volatile("mov.u32 %0, %0;" : "+r"(desc_sa));
   const uint32_t c3 = ((uint32_t)d.ctrl->iter << 8) | (uint32_t)PUR_Z;
+#pragma unroll
+  for (int n = 0; n < ES; ++n) Esm[n * 32 + lane] = (T)0;          // signatures >= N of a column stay zero
+  const uint32_t ediv = ((1u << 20) + (unsigned)N - 1u) / (unsigned)N;   // i / N = (i * ediv) >> 20 for i < 2048
 #pragma unroll
   for (int n = 0; n < TR; ++n) thr[n * 32 + lane] = 0xffffffffu;   // entries >= N-1 stay "never"
 #pragma unroll
@@ -586,22 +632,43 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
     const bool valid = g < G;
     const unsigned long long cell0 = (unsigned long long)K * (unsigned long long)(d.g0 + (long long)ct * 32);
 
-    // E tile of the item (a coalesced 16-byte-chunk load + scatter was measured: slower -- 40 live registers and a
-    // 16-way bank conflict on the scatter cost more than the sector efficiency gains)
+    // E tile of the item: N * 32 contiguous elements, copied as they lie (coalesced), a genome's column padded to ES
+    {
+      const T* __restrict__ Eg = d.E + (long long)N * ((long long)ct * 32);
+      const int n_el = N * min(32, G - ct * 32);              // elements of the tile that exist
+#ifdef BNMF_Z_EFULL
+#pragma unroll
+#else
 #pragma unroll 4
-    for (int n = 0; n < NP; ++n) Esm[n * 32 + lane] = (valid && n < N) ? d.E[(long long)n + (long long)N * g] : (T)0;
-    double a_sse = 0.0, a_kl = 0.0, a_ll = 0.0;
-    int sp_prev0 = 0, sp_prev1 = 0;     // lane n: sum over the tile's cells of hist[n][.] after the previous row
-
+#endif
+      for (int jj = 0; jj < NP; ++jj) {
+        const int i = jj * 32 + lane;
+        if (i < N * 32) {
+          const uint32_t c = ((uint32_t)i * ediv) >> 20;      // genome of element i; its signature is i - c N
+          Esm[i + (int)c * (ES - N)] = i < n_el ? Eg[i] : (T)0;
+        }
+      }
+    }
     // chunk rt = the mutation types of rank rt, rt + rts, rt + 2 rts, ... in `korder` (descending total count):
     // every chunk holds a like share of heavy and light types, so items weigh alike; heaviest row first
     int k = d.korder[rt];
     T p0 = use0 ? d.P[(long long)k + (long long)K * lane] : (T)0, p1 = (T)0;
     if (NP > 32) p1 = use1 ? d.P[(long long)k + (long long)K * (lane + 32)] : (T)0;
+#ifndef BNMF_Z_NO_MNEXT
+    int m_next = valid ? ZM(g, k) : 0;
+#endif
+    double a_sse = 0.0, a_kl = 0.0, a_ll = 0.0;
+    int sp_prev0 = 0, sp_prev1 = 0;     // lane n: sum over the tile's cells of hist[n][.] after the previous row
+
     for (int r = 0; r < ZR && r * rts + rt < K; ++r) {
-      const int m = valid ? d.Mi[(long long)k + (long long)K * g] : 0;
+#ifdef BNMF_Z_NO_MNEXT
+      const int m = valid ? ZM(g, k) : 0;
+#else
+      const int m = m_next;
+#endif
       const int k_this = k;
-      {   // row k of P into the warp's shared memory (read by every lane in phase 1); the next row's is on its way
+      {   // row k of P into the warp's shared memory (read by every lane in phase 1); the next row's (and the next
+          // row's counts) are on their way
         if (lane < NP) Prow[lane] = p0;
         if (NP > 32) { if (lane + 32 < NP) Prow[lane + 32] = p1; }
         __syncwarp();
@@ -609,12 +676,15 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
           k = d.korder[(r + 1) * rts + rt];
           p0 = use0 ? d.P[(long long)k + (long long)K * lane] : (T)0;
           if (NP > 32) p1 = use1 ? d.P[(long long)k + (long long)K * (lane + 32)] : (T)0;
+#ifndef BNMF_Z_NO_MNEXT
+          m_next = valid ? ZM(g, k) : 0;
+#endif
         }
       }
       // ---- phase 1: total of this lane's cell, metric partials ----
       T total = (T)0;
 #pragma unroll
-      for (int n = 0; n < NP; ++n) total = add_rn<T>(total, mul_rn<T>(Prow[n], Esm[n * 32 + lane]));
+      for (int n = 0; n < NP; ++n) total = add_rn<T>(total, mul_rn<T>(Prow[n], Esm[lane * ES + n]));
       if (valid && split == 0) {
         const double mh = (double)total;
         const double lam = mh > 1e-6 ? mh : 1e-6;
@@ -635,7 +705,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
         T acc = (T)0;
 #pragma unroll
         for (int n = 0; n < NP - 1; ++n) {
-          acc = add_rn<T>(acc, mul_rn<T>(Prow[n], Esm[n * 32 + lane]));
+          acc = add_rn<T>(acc, mul_rn<T>(Prow[n], Esm[lane * ES + n]));
           thr[n * 32 + lane] = n < N - 1 ? pick_thr(mul_rn<T>(acc, scale)) : 0xffffffffu;
         }
       }
@@ -746,6 +816,7 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
           const int run = F ? __ffs((int)~above) - 1 : 0;          // lanes lane+1 .. lane+run continue my first cell
           const int maxrun = __reduce_max_sync(0xffffffffu, run);
           const bool head = F && !chain;
+#ifdef BNMF_Z_OLD_FIXUP
 #pragma unroll
           for (int n = 0; n < NP; ++n) {
             int v = cont[n * 32 + lane];
@@ -756,6 +827,14 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
             }
             if (head && v) hist[n * 32 + c_first] += v;
           }
+#else
+          // straight-line code per number of doubling steps the longest chain of the row needs
+          if (maxrun == 0) zstat_fixup<NP, 0>(cont, hist, lane, F, head, run, c_first);
+          else if (maxrun == 1) zstat_fixup<NP, 1>(cont, hist, lane, F, head, run, c_first);
+          else if (maxrun < 4) zstat_fixup<NP, 2>(cont, hist, lane, F, head, run, c_first);
+          else if (maxrun < 8) zstat_fixup<NP, 3>(cont, hist, lane, F, head, run, c_first);
+          else zstat_fixup<NP, 5>(cont, hist, lane, F, head, run, c_first);
+#endif
           __syncwarp();
         }
       }

@@ -60,6 +60,7 @@ template <typename T> struct Dev {
 
   // data
   const int32_t* Mi;        // K x G counts (Poisson)
+  const int32_t* Mt;        // G x K: the same, genome-major (k_zstat reads the counts of 32 genomes as one line)
   const int32_t* korder;    // K: mutation types by descending total count (the order k_zstat visits them in)
   const T* Mr;              // K x G reals  (Normal)
   double ll_const;          // - sum lgamma(M+1) over THIS shard's columns (Poisson)
