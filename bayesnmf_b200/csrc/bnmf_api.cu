@@ -1217,8 +1217,8 @@ struct Sampler : bnmf_handle {
   int launch_iteration(bool wantP, bool wantA, cudaEvent_t z0, cudaEvent_t z1) {
     const long long KN = (long long)cfg.K * cfg.N;
     // (iterations replayed from a graph keep k_begin_iter: their side-branch kernels read the device's counter)
-    static const bool nofold = getenv("BNMF_FOLD_BEGIN") && !strcmp(getenv("BNMF_FOLD_BEGIN"), "0");
-    const bool fold_begin = !nofold && cfg.likelihood == BNMF_POISSON && !cfg.MH && !graphs_allowed();
+    const char* nf = getenv("BNMF_FOLD_BEGIN");      // "0": k_begin_iter as a launch of its own (tests compare the two)
+    const bool fold_begin = !(nf && !strcmp(nf, "0")) && cfg.likelihood == BNMF_POISSON && !cfg.MH && !graphs_allowed();
     if (!fold_begin) { k_begin_iter<T><<<1, 64, 0, stream>>>(d, work_ctr, n_ktiles); mark("k_begin_iter"); ++launches; }
     if (cfg.likelihood == BNMF_POISSON && !cfg.MH) { if (poisson_iteration(0, 0, z0, z1, fold_begin)) return 1; }
     else { if (mh_iteration(0, 0)) return 1; }

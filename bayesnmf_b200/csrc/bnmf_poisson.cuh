@@ -552,9 +552,16 @@ template <typename T> __host__ __device__ inline size_t zstat_smem_bytes(int NP,
 // column tile -- the tail of the launch -- are its lightest.
 // counts of genome g (local), mutation type k: the genome-major copy (a row of 32 genomes is one line)
 #ifdef BNMF_Z_NO_MT
-#define ZM(g, k) d.Mi[(long long)(k) + (long long)K * (g)]
+#define ZM(g, k) ZLD(&d.Mi[(long long)(k) + (long long)K * (g)])
 #else
-#define ZM(g, k) d.Mt[(long long)(g) + (long long)G * (k)]
+#define ZM(g, k) ZLD(&d.Mt[(long long)(g) + (long long)G * (k)])
+#endif
+// streamed operands (an element of E or M is read once per item): with 2 x 112 KB of shared memory the SM's L1 is
+// a few KB -- it is left to the rows of P, which every warp rereads
+#ifdef BNMF_Z_LDCG
+#define ZLD(p) __ldcg(p)
+#else
+#define ZLD(p) (*(p))
 #endif
 template <typename T, int NP, int MODE /* 0 dense, 1 sparse rows drawn lane-per-cell, 2 dense with several warps per item */>
 #ifndef ZV_REGS
@@ -636,16 +643,16 @@ k_zstat(Dev<T> d, const __grid_constant__ ZKeys rk, int ZR_A, int ZR_B, int ctA,
     {
       const T* __restrict__ Eg = d.E + (long long)N * ((long long)ct * 32);
       const int n_el = N * min(32, G - ct * 32);              // elements of the tile that exist
-#ifdef BNMF_Z_EFULL
-#pragma unroll
-#else
-#pragma unroll 4
+#ifndef BNMF_Z_EUNROLL
+#define BNMF_Z_EUNROLL 4
 #endif
+      constexpr int EU = BNMF_Z_EUNROLL;     // loads in flight per lane (all NP at once was measured: 6 % slower overall)
+#pragma unroll EU
       for (int jj = 0; jj < NP; ++jj) {
         const int i = jj * 32 + lane;
         if (i < N * 32) {
           const uint32_t c = ((uint32_t)i * ediv) >> 20;      // genome of element i; its signature is i - c N
-          Esm[i + (int)c * (ES - N)] = i < n_el ? Eg[i] : (T)0;
+          Esm[i + (int)c * (ES - N)] = i < n_el ? ZLD(Eg + i) : (T)0;
         }
       }
     }

@@ -27,7 +27,10 @@ if __name__ == "__main__":
             np.save(f, np_M)
         for lib in libs:
             env = dict(os.environ)
+            lib, _, kv = lib.partition("@")                      # lib@ENV=value,ENV=value: tuning knobs of the library
+            for e in filter(None, kv.split(",")):
+                env[e.split("=")[0]] = e.split("=")[1]
             if lib != "-": env["BNMF_LIB"] = os.path.join(ROOT, lib)
             else: env.pop("BNMF_LIB", None)
             r = subprocess.run([sys.executable, "-c", CHILD, f], env=env, capture_output=True, text=True, timeout=300)
-            print(f"mu={mu:g} G={G} lib={lib}: min/median ms, sum(SP) = {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
+            print(f"mu={mu:g} G={G} lib={lib} {kv}: min/median ms, sum(SP) = {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
