@@ -475,7 +475,12 @@ struct Sampler : bnmf_handle {
     ZR_B = 2; if (ZR_B > K) ZR_B = K;
     z_ctB = (int)std::min<long long>(cts / 2, (4LL * 148 * 16 + (K + ZR_B - 1) / ZR_B - 1) / ((K + ZR_B - 1) / ZR_B));
     ZR = 16;
-    while (ZR > 1 && (long long)(cts - z_ctB) * ((K + ZR - 1) / ZR) < 4000LL) ZR >>= 1;
+    // (a 12,500-genome shard: 8 rows 0.193 ms, 4 rows 0.197, 16 rows 0.211; 25,000 genomes: 8 rows 0.344, 16 rows 0.350, 4 rows 0.363)
+    {
+      auto coarse_items = [&](int zr) { return (long long)(cts - z_ctB) * ((K + zr - 1) / zr); };
+      if (coarse_items(16) < 4000LL) ZR = 8;
+      while (ZR > 1 && coarse_items(ZR) < 2300LL) ZR >>= 1;
+    }
     if (const char* e = getenv("BNMF_ZR")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ZR = v; }   // tuning knobs
     if (const char* e = getenv("BNMF_ZR_B")) { const int v = atoi(e); if (v >= 1 && v <= 32) ZR_B = v; }
     if (const char* e = getenv("BNMF_Z_CTB")) { const int v = atoi(e); if (v >= 0 && v <= cts) z_ctB = v; }
@@ -704,6 +709,7 @@ struct Sampler : bnmf_handle {
     return fail("k_zstat: unsupported padded signature count %d", NP);
   }
   int z_config() {
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, cfg.device);
     if (z_smem > 227 * 1024) return fail("k_zstat: %zu bytes of shared memory needed (N %d)", z_smem, cfg.N);
     return z_dispatch(true);
   }
@@ -1011,6 +1017,18 @@ struct Sampler : bnmf_handle {
   double* alpha_retry = nullptr; int* alpha_n_retry = nullptr; int alpha_cap = 0;   // parked Alpha_e envelopes (k_eside_hyper -> k_alpha_retry)
   bool hyper_ready = false, spec_next = false;
   int h_iter = 0;
+  unsigned long long* sides_pub = nullptr; unsigned long long sides_seq = 0;     // k_sides: "colSums(P) are out" counter
+  // k_sides when every block of it is resident at once (4 blocks of 512 threads per SM): measured on a 12,500-genome
+  // shard 261.7 -> 257.2 us per iteration, at 25,000 genomes 448.3 -> 447.7, at 100,000 (seven waves; the P-side
+  // blocks share their SMs with E-side blocks and the first wave waits for them) 1,580 -> 1,592: not used there.
+  // BNMF_SIDES = "0": never, "1": always.
+  bool sides_ok() const {
+    const char* e = getenv("BNMF_SIDES");
+    if (e && !strcmp(e, "0")) return false;
+    if (e && !strcmp(e, "1")) return true;
+    return (long long)cfg.N + d.n_eblocks <= 4LL * n_sms;
+  }
+  int n_sms = 148;
   bool overlap_allowed() const {
     static const bool off = getenv("BNMF_OVERLAP") && !strcmp(getenv("BNMF_OVERLAP"), "0");
     return !off && side != nullptr && cfg.prior == BNMF_GAMMA && cfg.likelihood == BNMF_POISSON && !cfg.MH && !graphs_allowed();
@@ -1054,6 +1072,17 @@ struct Sampler : bnmf_handle {
                 launches += 3;
                 break;
               }
+              if (hyper_ready && fold_begin && sides_ok() && !keepP && !keepE) {
+                // steady state: both sides' hyper-draws were made under the previous k_zstat -- the P side, the E side
+                // and k_begin_iter are one launch (k_sides)
+                CK(cudaStreamWaitEvent(stream, ev_join_p, 0));
+                CK(cudaStreamWaitEvent(stream, ev_join, 0));
+                if (!sides_pub) { if (dalloc(&sides_pub, 1)) return 1; sides_seq = 0; }
+                ++sides_seq;
+                k_sides<T, ET><<<cfg.N + d.n_eblocks, ET, 0, stream>>>(d, h_iter, bc, bn, bt, sides_pub, (unsigned long long)cfg.N * sides_seq); mark("k_sides");
+                hyper_ready = false;
+                --launches;               // (one launch where the count below expects two)
+              } else {
               if (hyper_ready) {          // Beta_p / Alpha_p of this iteration were drawn under the previous k_zstat
                 CK(cudaStreamWaitEvent(stream, ev_join_p, 0));
                 k_pside<T, 128, PRIOR_GAMMA, 0, 1><<<cfg.N, 128, 0, stream>>>(d, keepP, bc, bn, bt); mark("k_pside");
@@ -1063,6 +1092,7 @@ struct Sampler : bnmf_handle {
                 k_eside<T, ET, PRIOR_GAMMA, 0, 1><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside");
                 hyper_ready = false;
               } else k_eside<T, ET, PRIOR_GAMMA, 0><<<d.n_eblocks, ET, 0, stream>>>(d, keepE); mark("k_eside");
+              }
               if (spec_next && overlap_allowed()) {
                 if (!alpha_retry) {      // list of parked Alpha_e cells, a quarter of the cells long: 16 % are rejected once, an
                                          // overflowing cell finishes in place (allocated -- zero-filled on `stream` -- before the fork)
@@ -1276,17 +1306,20 @@ struct Sampler : bnmf_handle {
       // ctrl.converged / ctrl.row for this chunk (iter and ring position live on the device)
       int two[2] = {converged, -1};
       CK(cudaMemcpyAsync(&d.ctrl->converged, two, sizeof(two), cudaMemcpyHostToDevice, stream));
-      const bool timez = !use_graph && time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
+      // per-iteration / per-k_zstat events (bnmf_timing's iter_ms, zstat_ms): four event records per iteration
+      const char* tev = getenv("BNMF_TIMING");
+      const bool timei = !(tev && !strcmp(tev, "0"));
+      const bool timez = timei && !use_graph && time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
       if (timez) while ((int)zev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); zev.push_back(e); }
-      while ((int)iev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); iev.push_back(e); }
+      if (timei) while ((int)iev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); iev.push_back(e); }
       for (int i = 0; i < chunk; ++i) {
         if (flush_bytes) CK(cudaMemsetAsync(flush_buf, i & 0xff, flush_bytes, stream));
-        CK(cudaEventRecord(iev[2 * i], stream));
+        if (timei) CK(cudaEventRecord(iev[2 * i], stream));
         spec_next = done + i + 1 < n_iters;     // never past the end of this call: the state handed back is iteration n's
         ++h_iter;
         if (use_graph) { CK(cudaGraphLaunch(gexec, stream)); launches += glaunches; }
         else if (launch_iteration(P_out != nullptr, A_out != nullptr, timez ? zev[2 * i] : nullptr, timez ? zev[2 * i + 1] : nullptr)) return 1;
-        CK(cudaEventRecord(iev[2 * i + 1], stream));
+        if (timei) CK(cudaEventRecord(iev[2 * i + 1], stream));
       }
       CK(cudaMemcpyAsync(h_metrics, d.metrics, sizeof(double) * MC_COLS * chunk, cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
@@ -1298,7 +1331,7 @@ struct Sampler : bnmf_handle {
       if (P_out) { if (dev_to_host(P_hist, ST_T, (long long)chunk * KN, P_out + (long long)done * KN)) return 1; }
       if (A_out) { if (dev_to_host(A_hist, ST_I32, (long long)chunk * N, A_out + (long long)done * N)) return 1; }
       if (timez) for (int i = 0; i < chunk; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, zev[2 * i], zev[2 * i + 1])); last_z_ms += ms; }
-      for (int i = 0; i < chunk; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, iev[2 * i], iev[2 * i + 1])); last_iter_ms += ms; }
+      if (timei) for (int i = 0; i < chunk; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, iev[2 * i], iev[2 * i + 1])); last_iter_ms += ms; }
       done += chunk;
     }
     CK(cudaEventRecord(ev1, stream));

@@ -19,6 +19,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+
 // block-wide deterministic sum of one double per thread; result valid in thread 0.
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double* scratch /*THREADS/32*/) {
@@ -361,6 +365,100 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_eside(Dev<T> d, int
   }
   if (threadIdx.x == 0) {
     double* ep = d.epart + (long long)blockIdx.x * PC_COLS;
+    ep[PC_SSE] = 0.0; ep[PC_KLV] = 0.0; ep[PC_LLV] = 0.0; ep[PC_LP_E] = lps; ep[PC_EACC] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------
+// k_sides: k_pside and k_eside of a steady-state iteration of the gamma-prior model (hyper-draws already made on
+// the side stream) as ONE launch.  Blocks [0, N) are the P side (block n = signature n, as k_pside); the others
+// are the E side (as k_eside): they form everything of their draw that does not need the column sums of the new
+// P -- the loads, the unit-rate Gamma variate (its shape is Alpha_e + SE) -- and only then wait for the N P-side
+// blocks to have published colSums(P) (a counter that grows by N per launch: nothing to reset; blocks are handed
+// out in index order, the P-side blocks are resident before any block that waits for them).  One launch and the
+// P side's latency less on the chain exchange -> P -> E -> Z of an iteration (an 8-GPU shard: ~8 us of 270).
+// `iter` comes by value: the launch is also k_begin_iter (k_pside's begin_ctr), whose update of the device's counter
+// the E-side blocks must not race with.  Draw for draw the two kernels it replaces.
+// ------------------------------------------------------------------------------
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+k_sides(Dev<T> d, int iter, int* begin_ctr, int n_ctr, unsigned* begin_ticket, unsigned long long* pub, unsigned long long pub_target) {
+  __shared__ double scratch[THREADS / 32];
+  __shared__ long long fx[THREADS];
+  const int K = d.K, N = d.N;
+  if ((int)blockIdx.x < N) {
+    // ---- P side of signature n (k_pside<T, THREADS, PRIOR_GAMMA, 0, 1>) ----
+    const int n = blockIdx.x;
+    const int An = d.A[n];
+    const double rsE = (double)d.rowsumE_fx[n] / RS_FX;
+    double csum = 0.0, lp = 0.0;
+    // the first 128 threads, 128 apart -- k_pside's assignment of mutation types to threads, so that the two sums
+    // below are formed in its order for any K (the other warps add zeros)
+    for (int k = threadIdx.x; k < K && threadIdx.x < 128; k += 128) {
+      const long long c = (long long)k + (long long)K * n;
+      const double al = (double)d.Alpha_p[c], be = (double)d.Beta_p[c];
+      const double Pnew = gamma_draw<double>(make_stream(d.seed, iter, PUR_P, c), al + (double)d.SP[c], be + (An ? rsE : 0.0));
+      lp += dgamma_log((double)(T)Pnew, (double)(T)al, (double)(T)be);
+      d.P[c] = (T)Pnew;
+      d.SP[c] = 0ull;
+      if (d.ring_cap > 0) d.ring_P[(long long)d.ctrl->ring_pos * K * N + c] = (T)Pnew;
+      csum += (double)(T)Pnew;
+    }
+    const double cs = block_sum<THREADS>(csum, scratch);
+    const double lps = block_sum<THREADS>(lp, scratch);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+      d.colsumP[n] = (T)cs;
+      d.rowsumE_fx[n] = 0ll;
+      d.zpart[(long long)(d.n_zitems) * PC_COLS + n] = lps;
+      __threadfence();
+      atomicAdd(pub, 1ull);                                   // colSums(P)[n] is out
+      last = atomicAdd(begin_ticket, 1u) == (unsigned)N - 1u;
+    }
+    __syncthreads();
+    if (!last) return;
+    // the last P-side block is k_begin_iter (no block of this launch reads the device's counter)
+    for (int i = threadIdx.x; i < n_ctr; i += THREADS) begin_ctr[i] = 0;
+    for (int j = threadIdx.x; j < N; j += THREADS) { d.nzP[j] = 0; d.nzE[(iter & 1) * N + j] = 0; }
+    if (threadIdx.x == 0) { d.ctrl->iter = iter; d.ctrl->row += 1; *d.lp_P = 0.0; *d.pacc_sum = 0.0; *begin_ticket = 0u; }
+    return;
+  }
+  // ---- E side (k_eside<T, THREADS, PRIOR_GAMMA, 0, 1>) ----
+  const int eb = (int)blockIdx.x - N;
+  const long long cells = (long long)N * d.G;
+  const long long base = (long long)eb * THREADS;
+  const long long idx = base + threadIdx.x;
+  const bool act = idx < cells;
+  const long long ii = act ? idx : cells - 1;
+  const int n = (int)(ii % N);
+  const long long c = (long long)n + (long long)N * (d.g0 + ii / N);  // global cell id
+  const int An = d.A[n];
+  const double al = (double)d.Alpha_e[ii], be = (double)d.Beta_e[ii];
+  const double g0 = gamma_unit<double>(make_stream(d.seed, iter, PUR_E, c), al + (double)d.SE[ii]);
+  if (threadIdx.x == 0) {
+    while (ld_acquire_gpu_u64(pub) < pub_target) __nanosleep(20);
+  }
+  __syncthreads();
+  const double csP = An ? (double)__ldcg(&d.colsumP[n]) : 0.0;
+  const double Enew = gamma_scale<double>(g0, be + csP);
+  double lp = dgamma_log((double)(T)Enew, (double)(T)al, (double)(T)be);
+  long long myfx = 0;
+  if (act) {
+    d.E[ii] = (T)Enew;
+    d.SE[ii] = 0;
+    if (d.ring_cap > 0) d.ring_E[(long long)d.ctrl->ring_pos * cells + ii] = (T)Enew;
+    myfx = llrint((double)(T)Enew * RS_FX);
+  } else lp = 0.0;
+  fx[threadIdx.x] = myfx;
+  const double lps = block_sum<THREADS>(lp, scratch);   // contains __syncthreads => fx visible
+  if (threadIdx.x < N) {
+    long long s = 0;
+    for (int o = threadIdx.x; o < THREADS; o += N) s += fx[o];
+    const int nn = (int)((base + threadIdx.x) % N);
+    atomicAdd((unsigned long long*)&d.rowsumE_fx[nn], (unsigned long long)s);
+  }
+  if (threadIdx.x == 0) {
+    double* ep = d.epart + (long long)eb * PC_COLS;
     ep[PC_SSE] = 0.0; ep[PC_KLV] = 0.0; ep[PC_LLV] = 0.0; ep[PC_LP_E] = lps; ep[PC_EACC] = 0.0;
   }
 }

@@ -138,7 +138,9 @@ template <typename T> BNMF_HD T normal_draw(const Stream& s, T mean, T sd) {
 // uniform, w -> boost uniform.  Result floored at the smallest normal so that a
 // later log() stays finite (R's rgamma can return exactly 0 for tiny shapes).
 // (stats::rgamma(n, shape, rate): R/sample_Pn.R:23-27,116-118, R/sample_priors.R:285-344)
-template <typename T> BNMF_HD_CALL T gamma_draw(const Stream s, T shape, T rate, uint32_t sub0 = 0) {
+// gamma_unit: the variate before the division by the rate (everything that needs the shape only; k_sides draws it
+// while the rate is still being formed); gamma_scale: the division and the floor.  gamma_draw = the two in a row.
+template <typename T> BNMF_HD_CALL T gamma_unit(const Stream s, T shape, uint32_t sub0 = 0) {
   const bool boost = shape < (T)1;
   const T a = boost ? shape + (T)1 : shape;
   const T d = a - (T)(1.0 / 3.0);
@@ -160,9 +162,15 @@ template <typename T> BNMF_HD_CALL T gamma_draw(const Stream s, T shape, T rate,
       break;
     }
   }
+  return g;
+}
+template <typename T> BNMF_HD T gamma_scale(T g, T rate) {
   g = g / rate;
   const T tiny = sizeof(T) == 8 ? (T)DBL_MIN : (T)FLT_MIN;
   return g < tiny ? tiny : g;
+}
+template <typename T> BNMF_HD T gamma_draw(const Stream s, T shape, T rate, uint32_t sub0 = 0) {
+  return gamma_scale<T>(gamma_unit<T>(s, shape, sub0), rate);
 }
 
 // Normal(mean, sd) truncated to [0, inf).  Every call site of truncnorm::rtruncnorm

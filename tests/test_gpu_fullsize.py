@@ -120,7 +120,8 @@ def test_overlapped_iterations_equal_sequential_ones(built_lib):
     cells parked and finished by k_alpha_retry).  One call of 5 iterations (overlapped) equals 5 calls
     of one iteration (a call's last iteration never speculates: the fused sequential kernels) bit for
     bit; so does a run whose parking list is too short (BNMF_ALPHA_CAP: the overflow path), and one whose
-    iterations start with k_begin_iter instead of having k_pside's last block do its work (BNMF_FOLD_BEGIN=0)."""
+    iterations start with k_begin_iter instead of having k_pside's last block do its work (BNMF_FOLD_BEGIN=0), and
+    one whose steady-state iterations launch k_pside and k_eside instead of the merged k_sides (BNMF_SIDES=0)."""
     from bayesnmf_b200 import Handle
     K, G, N = 96, 24_000, 8
     M, _, _ = synth_counts(K, G, N, 2000.0, seed=6)
@@ -143,10 +144,12 @@ def test_overlapped_iterations_equal_sequential_ones(built_lib):
     rows_a, st_a, l_a = chain([5])
     rows_b, st_b, l_b = chain([1] * 5)
     rows_c, st_c, _ = chain([5], {"BNMF_ALPHA_CAP": "16"})
-    rows_d, st_d, l_d = chain([5], {"BNMF_FOLD_BEGIN": "0"})     # k_begin_iter as a launch of its own, not inside k_pside
+    rows_d, st_d, l_d = chain([5], {"BNMF_FOLD_BEGIN": "0"})     # k_begin_iter, k_pside, k_eside: three launches
+    rows_e, st_e, l_e = chain([5], {"BNMF_SIDES": "0"})          # k_pside (+ k_begin_iter's work), k_eside: two launches
     assert l_a > l_b * 5            # the overlapped call launched the side-stream kernels, the single steps did not
-    assert l_d == l_a + 5
-    for rows, st in ((rows_b, st_b), (rows_c, st_c), (rows_d, st_d)):
+    assert l_e == l_a + 4           # iterations 2..5 of the call ran k_sides: one launch for the two sides
+    assert l_d == l_e + 5
+    for rows, st in ((rows_b, st_b), (rows_c, st_c), (rows_d, st_d), (rows_e, st_e)):
         np.testing.assert_array_equal(rows_a, rows)
         for n in names:
             np.testing.assert_array_equal(st_a[n], st[n], err_msg=n)
