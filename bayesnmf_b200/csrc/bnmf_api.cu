@@ -1306,10 +1306,14 @@ struct Sampler : bnmf_handle {
       // ctrl.converged / ctrl.row for this chunk (iter and ring position live on the device)
       int two[2] = {converged, -1};
       CK(cudaMemcpyAsync(&d.ctrl->converged, two, sizeof(two), cudaMemcpyHostToDevice, stream));
-      // per-iteration / per-k_zstat events (bnmf_timing's iter_ms, zstat_ms): four event records per iteration
+      // bnmf_timing's iter_ms: two event records per iteration, at its boundaries; zstat_ms: two more INSIDE the
+      // chain of an iteration, on either side of k_zstat (together 2 us of a 257 us shard iteration, 10 of 1,580 at
+      // C3) -- recorded with the L2 flush (benchmark mode) or when asked for.  BNMF_TIMING = "0": no events,
+      // "iter": the iteration's only, "z": both
       const char* tev = getenv("BNMF_TIMING");
       const bool timei = !(tev && !strcmp(tev, "0"));
-      const bool timez = timei && !use_graph && time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
+      const bool wantz = tev ? !strcmp(tev, "z") : flush_bytes > 0;
+      const bool timez = timei && wantz && !use_graph && time_z && cfg.likelihood == BNMF_POISSON && !cfg.MH;
       if (timez) while ((int)zev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); zev.push_back(e); }
       if (timei) while ((int)iev.size() < 2 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); iev.push_back(e); }
       for (int i = 0; i < chunk; ++i) {

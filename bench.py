@@ -230,13 +230,20 @@ def run_b200(args):
         time.sleep(0.25)
         sync()
         t0 = time.time()
+        os.environ["BNMF_TIMING"] = "iter"       # events at the iterations' boundaries only (none inside their chain)
         out = h.step(args.steps)
+        os.environ.pop("BNMF_TIMING")
         sync()
         t1 = time.time()
     tm = h.timing()
     clocks = cs.summary(t0, t1)
-    iter_ms, z_ms = rmax(tm["iter_ms"], tm["zstat_ms"])
+    iter_ms, = rmax(tm["iter_ms"])
     ms_per_step = iter_ms / args.steps
+    # the latent-count kernel's launches inside an iteration (events on either side of it): a pass of their own
+    z_steps = min(args.steps, 20)
+    h.step(z_steps)
+    z_ms, = rmax(h.timing()["zstat_ms"])
+    z_ms *= args.steps / z_steps
     n_chains = 1 if sharded else world
     value = n_chains * 1e3 / ms_per_step
     launches = int(tm["launches"])
@@ -348,6 +355,16 @@ def run_b200(args):
                                  "frac": iach / ipeak, "warp_insts_per_launch": ncu["warp_insts_per_launch"],
                                  "thread_insts_per_pick": 32.0 * ncu["warp_insts_per_launch"] / picks if picks else None,
                                  "source": "ncu smsp__inst_executed.sum (profiles/traffic.json) / CUDA-event time of the kernel alone"}
+    if roof_kernel in ("k_p_rows", "k_e_sweep") and w["likelihood"] == "poisson" and k_ms:
+        # the roof that governs the Poisson + MH sweeps: the fp64 pipe.  A cell (k, n, g) of a sweep costs one fp64
+        # reciprocal (~11 instructions), the residual, two products into two sums and the rank-1 update of Mhat:
+        # ~24 fp64 instructions, K N G cells per side
+        f_hz = 1e6 * (clocks.get("sm_mhz") or sm_max_mhz)
+        dpeak = 148 * 64 * f_hz
+        dach = 24.0 * K * N * G_loc / (k_ms * 1e-3)
+        roofline["fp64"] = {"bound": "fp64 pipe", "achieved": dach / 1e12, "peak": dpeak / 1e12, "unit": "T fp64-inst/s",
+                            "frac": dach / dpeak, "fp64_insts_per_cell": 24,
+                            "source": "algorithmic count (one reciprocal + residual + two sums + rank-1 update per cell and signature) / CUDA-event time of the kernel"}
     res = {
         "metric": metric_name(w), "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak",

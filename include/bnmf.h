@@ -195,7 +195,8 @@ int bnmf_comm_share(bnmf_handle* h, bnmf_handle* src);
 /* Device timing of the last bnmf_step call (CUDA events on the handle's stream), in
  * milliseconds: total = the whole call; iter = sum over iterations of the span from
  * the first to the last kernel of the iteration; zstat = share of the latent-count
- * kernel; launches = kernels launched. */
+ * kernel (events inside the iteration's chain: recorded when the L2 flush below is on
+ * or the environment says BNMF_TIMING=z, else 0); launches = kernels launched. */
 int bnmf_timing(bnmf_handle* h, double* total_ms, double* iter_ms, double* zstat_ms, int64_t* launches);
 
 /* Benchmark hygiene: when bytes > 0, bnmf_step overwrites a scratch buffer of that size

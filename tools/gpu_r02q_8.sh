@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, final 8-GPU call: the sharded bench at N = 8 (and 4)
+mkdir -p gpurun_out
+TAG=r02q
+run() { # N, workload
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $1 --steps 50 --warmup 5 --no-cpu-baseline --workload $2 2> gpurun_out/bench_$2_n$1_$TAG.err > gpurun_out/bench_$2_n$1_$TAG.json
+  python - <<PY
+import json
+j=json.load(open("gpurun_out/bench_$2_n$1_$TAG.json")); print("$2 N=$1:", round(j["value"],1), "it/s  e2e", round(j["e2e"]["value"],1), "ms/step", round(j["ms_per_step"],4), "warm", round(j.get("value_l2_warm",0),1), j.get("kernels_ms_per_step"), "z alone", j["roofline"].get("launch_ms_kernel_alone"), "z in-step", j["roofline"].get("avg_launch_ms"))
+PY
+}
+run 8 c3
+run 4 c3

@@ -17,7 +17,7 @@ for k, v in fill_hyperprior_params(None, "gamma", float(M.mean()), 20).items():
     h.set_hyper(k, v)
 h.init_from_prior()
 h.step(50)
-variants = {"default": {}, "no timing events": {"BNMF_TIMING": "0"}, "two launches": {"BNMF_SIDES": "0"}, "k_sides forced": {"BNMF_SIDES": "1"}}
+variants = {"default": {}, "no timing events": {"BNMF_TIMING": "0"}, "z events too": {"BNMF_TIMING": "z"}, "two launches": {"BNMF_SIDES": "0"}, "k_sides forced": {"BNMF_SIDES": "1"}}
 for a in sys.argv[3:]:                                  # extra variants: name:ENV=v,ENV=v
     nm, _, kv = a.partition(":")
     variants[nm] = dict(e.split("=") for e in kv.split(","))
