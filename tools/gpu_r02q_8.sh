@@ -10,4 +10,4 @@ j=json.load(open("gpurun_out/bench_$2_n$1_$TAG.json")); print("$2 N=$1:", round(
 PY
 }
 run 8 c3
-run 4 c3
+
