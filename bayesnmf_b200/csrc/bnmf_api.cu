@@ -1018,7 +1018,7 @@ struct Sampler : bnmf_handle {
   bool hyper_ready = false, spec_next = false;
   int h_iter = 0;
   unsigned long long* sides_pub = nullptr; unsigned long long sides_seq = 0;     // k_sides: "colSums(P) are out" counter
-  // k_sides when every block of it is resident at once (4 blocks of 512 threads per SM): measured on a 12,500-genome
+  // k_sides on small shards -- at most two waves of its blocks (512 threads at 64 registers: two per SM): measured on a 12,500-genome
   // shard 261.7 -> 257.2 us per iteration, at 25,000 genomes 448.3 -> 447.7, at 100,000 (seven waves; the P-side
   // blocks share their SMs with E-side blocks and the first wave waits for them) 1,580 -> 1,592: not used there.
   // BNMF_SIDES = "0": never, "1": always.
