@@ -40,6 +40,7 @@ def _worker(rank, world, port, out_dir, prior, learn):
         return t.numpy()
 
     mean = global_mean(M[:, lo:hi], dist)
+    mean_ls = global_mean(M[:, lo:hi], dist, local_sum=float(M[:, lo:hi].sum()))   # the sum bnmf_create hands back ('data_sum')
     uid = broadcast_bytes(bytes(range(128)) if rank == 0 else b"", 128, dist)     # how the NCCL id travels
     o = OracleSampler(M[:, lo:hi], 4, "poisson", prior, MH=False, seed=5, g0=lo, G_total=M.shape[1], mean_data=mean,
                       learning_rank=learn, temperature_schedule=get_temp_sched(40, 10) if learn else None, reduce_fn=reduce_fn)
@@ -47,7 +48,7 @@ def _worker(rank, world, port, out_dir, prior, learn):
         o.step()
     with open(os.path.join(out_dir, f"r{rank}.pkl"), "wb") as f:
         pickle.dump(dict(P=o.params["P"], E=o.params["E"], A=o.params["A"], SP=o.SP, SE=o.SE, metrics=o.metrics,
-                         mean=mean, uid=uid, lo=lo, hi=hi), f)
+                         mean=mean, mean_ls=mean_ls, uid=uid, lo=lo, hi=hi), f)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,6 +69,7 @@ def test_two_rank_gloo_equals_single(prior, learn):
         ref.step()
     assert parts[0]["uid"] == parts[1]["uid"] == bytes(range(128))
     np.testing.assert_allclose(parts[0]["mean"], M.mean(), rtol=1e-14)
+    assert parts[0]["mean_ls"] == parts[0]["mean"] == parts[1]["mean"] == parts[1]["mean_ls"]
     for p in parts:
         np.testing.assert_array_equal(p["SP"], ref.SP)                      # integer sums: exact
         np.testing.assert_array_equal(p["P"], ref.params["P"])              # replicated, bit-identical
